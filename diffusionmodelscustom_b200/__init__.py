@@ -1,0 +1,12 @@
+"""B200-native DDPM reverse-diffusion sampling for the DANRA conditional UNets of TheaQG/DiffusionModelsCustom.
+
+Public surface = the reference's own:
+    from diffusionmodelscustom_b200 import Encoder, Decoder, DiffusionNet, DiffusionUtils
+plus the north_star aliases ``UNet`` and ``Diffusion``.  Everything executes in ``libb200ddpm.so`` (hand-written
+sm_100a CUDA behind the C ABI of ``include/b200ddpm.h``); there is no eager/CPU fallback.
+"""
+from .modules import Decoder, DecoderBlock, DiffusionNet, Encoder, ImageSelfAttention, SinusoidalEmbedding, UNet  # noqa: F401
+from .diffusion import Diffusion, DiffusionUtils, DiffusionUtilsV2  # noqa: F401
+
+__all__ = ["Encoder", "Decoder", "DecoderBlock", "DiffusionNet", "ImageSelfAttention", "SinusoidalEmbedding", "UNet",
+           "DiffusionUtils", "DiffusionUtilsV2", "Diffusion"]

@@ -1,0 +1,326 @@
+// Self-attention pieces for ImageSelfAttention (modules_DANRA_conditional.py:91-110) / SelfAttention (unet_ms.py:21-27).
+//
+// NHWC activations are already the (B, L=H*W, C) token layout, so no permutes exist on this path.
+//   layernorm_rows_kernel : LayerNorm over C per token, fp32 statistics, one warp per token.
+//   flash_attn_kernel     : softmax(q k^T / sqrt(d)) v per (sample, head) with streaming (online) softmax —
+//                           the L x L score matrix the reference materialises (need_weights=True) never exists.
+//                           mma.sync m16n8k16 bf16 (these layers are ex2-bound at head_dim 16),
+//                           K/V tiles double-buffered in shared memory with cp.async.
+// The QKV and output projections run through the tcgen05 GEMM path (conv.cuh, 1x1 case) with the residual add
+// (+ ReLU in the decoder) in its epilogue.
+#pragma once
+#include "common.cuh"
+
+namespace b2d {
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// x,y: [rows][C] bf16.  C in {64,...,512}, C % 64 == 0.  One warp per row, each lane owns C/32 contiguous pairs.
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, bf16* __restrict__ y,
+                                                             int rows) {
+    constexpr int PER = C / 32;  // elements per lane (2..16), contiguous
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const bf16* xr = x + (size_t)warp * C + lane * PER;
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) {
+        const float2 t = __bfloat1622float2(*reinterpret_cast<const bf162*>(xr + i));
+        v[i] = t.x;
+        v[i + 1] = t.y;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / C);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const float d = v[i] - mean;
+        ss += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + 1e-5f);
+    bf16* yr = y + (size_t)warp * C + lane * PER;
+#pragma unroll
+    for (int i = 0; i < PER; i += 2) {
+        const int c = lane * PER + i;
+        const float a = (v[i] - mean) * rstd * gamma[c] + beta[c];
+        const float b = (v[i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1];
+        *reinterpret_cast<bf162*>(yr + i) = __floats2bfloat162_rn(a, b);
+    }
+}
+
+inline int layernorm_launch(const bf16* x, const float* g, const float* b, bf16* y, int rows, int C, cudaStream_t st) {
+    const int blocks = (rows + 7) / 8;
+    switch (C) {
+        case 64: layernorm_rows_kernel<64><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
+        case 128: layernorm_rows_kernel<128><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
+        case 256: layernorm_rows_kernel<256><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
+        case 512: layernorm_rows_kernel<512><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
+        default: return fail(-1, "layernorm: unsupported channel count " + std::to_string(C));
+    }
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ flash attention
+// qkv: [B*L][3C] bf16 (q | k | v, head j owns columns [j*D,(j+1)*D) of each third); o: [B*L][C] bf16.
+// grid = (ceil(L/64), heads, B); 128 threads; each warp owns 16 query rows; KV tiles of 64 keys.
+constexpr int FA_BQ = 64;
+constexpr int FA_BK = 64;
+
+template <int D>
+__host__ __device__ constexpr int fa_smem_bytes() {
+    return 2 /*stages*/ * 2 /*K,V*/ * FA_BK * (D + 8) * 2;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int C,
+                                                         float scale_log2e) {
+    constexpr int LDS = D + 8;  // padded row (elements): conflict-free 32-bit fragment loads and ldmatrix
+    extern __shared__ __align__(16) uint8_t fa_smem[];
+    bf16* sK = reinterpret_cast<bf16*>(fa_smem);          // [2][FA_BK][LDS]
+    bf16* sV = sK + 2 * FA_BK * LDS;                      // [2][FA_BK][LDS]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int q0 = blockIdx.x * FA_BQ + warp * 16;
+    const size_t row_stride = (size_t)3 * C;
+    const bf16* base = qkv + (size_t)b * L * row_stride + (size_t)head * D;
+
+    // ---- Q fragments (A operand, 16 x D), rows q0+g and q0+g+8
+    uint32_t qf[D / 16][4];
+    {
+        const int r0 = q0 + g, r1 = q0 + g + 8;
+        const bf16* p0 = base + (size_t)r0 * row_stride;
+        const bf16* p1 = base + (size_t)r1 * row_stride;
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+            const int c = kk * 16 + 2 * t;
+            qf[kk][0] = r0 < L ? *reinterpret_cast<const uint32_t*>(p0 + c) : 0u;
+            qf[kk][1] = r1 < L ? *reinterpret_cast<const uint32_t*>(p1 + c) : 0u;
+            qf[kk][2] = r0 < L ? *reinterpret_cast<const uint32_t*>(p0 + c + 8) : 0u;
+            qf[kk][3] = r1 < L ? *reinterpret_cast<const uint32_t*>(p1 + c + 8) : 0u;
+        }
+    }
+
+    float oacc[D / 8][4];
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    const int ntiles = (L + FA_BK - 1) / FA_BK;
+    constexpr int CPR = D / 8;  // 16-byte chunks per row
+
+    auto load_tile = [&](int tile, int buf) {
+        const int k0 = tile * FA_BK;
+        bf16* dK = sK + buf * FA_BK * LDS;
+        bf16* dV = sV + buf * FA_BK * LDS;
+        for (int i = threadIdx.x; i < FA_BK * CPR; i += 128) {
+            const int r = i / CPR, c = (i - r * CPR) * 8;
+            const bool ok = (k0 + r) < L;
+            const bf16* src = base + (size_t)(ok ? (k0 + r) : 0) * row_stride + c;
+            cp_async16(dK + r * LDS + c, src + C, ok);
+            cp_async16(dV + r * LDS + c, src + 2 * C, ok);
+        }
+    };
+
+    load_tile(0, 0);
+    cp_async_commit();
+
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int buf = tile & 1;
+        if (tile + 1 < ntiles) load_tile(tile + 1, buf ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const bf16* tK = sK + buf * FA_BK * LDS;
+        const bf16* tV = sV + buf * FA_BK * LDS;
+
+        // ---- S = Q K^T (16 x 64 per warp), fp32
+        float s[FA_BK / 8][4];
+#pragma unroll
+        for (int j = 0; j < FA_BK / 8; ++j) {
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+            const bf16* kr = tK + (j * 8 + g) * LDS + 2 * t;
+#pragma unroll
+            for (int kk = 0; kk < D / 16; ++kk) {
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kk * 16);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8);
+                mma_bf16_16816(s[j], qf[kk], b0, b1);
+            }
+        }
+        // ---- mask keys beyond L (last tile only)
+        const int k0 = tile * FA_BK;
+        if (k0 + FA_BK > L) {
+#pragma unroll
+            for (int j = 0; j < FA_BK / 8; ++j) {
+                const int kc = k0 + j * 8 + 2 * t;
+                if (kc >= L) s[j][0] = s[j][2] = -INFINITY;
+                if (kc + 1 >= L) s[j][1] = s[j][3] = -INFINITY;
+            }
+        }
+        // ---- online softmax (rows g and g+8; a row is spread over the 4 lanes of a quad)
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int j = 0; j < FA_BK / 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float corr0 = ex2_approx((m0 - mx0) * scale_log2e);
+        const float corr1 = ex2_approx((m1 - mx1) * scale_log2e);
+        m0 = mx0;
+        m1 = mx1;
+        const float ms0 = mx0 * scale_log2e, ms1 = mx1 * scale_log2e;
+        float rs0 = 0.f, rs1 = 0.f;
+        uint32_t pf[FA_BK / 16][4];
+#pragma unroll
+        for (int j = 0; j < FA_BK / 8; ++j) {
+            const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -ms0));
+            const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -ms0));
+            const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, -ms1));
+            const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -ms1));
+            rs0 += p0 + p1;
+            rs1 += p2 + p3;
+            pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+            pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+        }
+        l0 = l0 * corr0 + rs0;
+        l1 = l1 * corr1 + rs1;
+#pragma unroll
+        for (int i = 0; i < D / 8; ++i) {
+            oacc[i][0] *= corr0;
+            oacc[i][1] *= corr0;
+            oacc[i][2] *= corr1;
+            oacc[i][3] *= corr1;
+        }
+        // ---- O += P V : A = P (from registers), B[k][n] = V[key k][dim n] via ldmatrix.trans
+#pragma unroll
+        for (int kk = 0; kk < FA_BK / 16; ++kk) {
+            const uint32_t vrow = smem_u32(tV + (kk * 16 + (lane & 15)) * LDS);
+#pragma unroll
+            for (int i = 0; i < D / 8; ++i) {
+                uint32_t b0, b1;
+                ldmatrix_x2_trans(b0, b1, vrow + i * 16);
+                mma_bf16_16816(oacc[i], pf[kk], b0, b1);
+            }
+        }
+        __syncthreads();  // everyone done with this buffer before it is refilled
+    }
+    cp_async_wait<0>();
+
+    // ---- finalise: row sums across the quad, normalise, store
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+    bf16* ob = o + (size_t)b * L * C + (size_t)head * D + 2 * t;
+#pragma unroll
+    for (int i = 0; i < D / 8; ++i) {
+        if (r0 < L)
+            *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * C + i * 8) = pack_bf16(oacc[i][0] * inv0, oacc[i][1] * inv0);
+        if (r1 < L)
+            *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * C + i * 8) = pack_bf16(oacc[i][2] * inv1, oacc[i][3] * inv1);
+    }
+}
+
+// Head dims below the m16n8k16 K extent (n_heads = 8 or H/2 in some reference scripts, e.g. test/unet_test.py:20-159):
+// one thread per query, K/V tiles of 128 keys in shared memory, online softmax in blocks of 8 keys.
+template <int D>
+__global__ void __launch_bounds__(128) attn_small_d_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int C,
+                                                           float scale_log2e) {
+    __shared__ float sK[128][D];
+    __shared__ float sV[128][D];
+    const int head = blockIdx.y, b = blockIdx.z;
+    const int qi = blockIdx.x * 128 + threadIdx.x;
+    const size_t rs = (size_t)3 * C;
+    const bf16* base = qkv + (size_t)b * L * rs + (size_t)head * D;
+    float q[D], acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        q[d] = qi < L ? __bfloat162float(base[(size_t)qi * rs + d]) * scale_log2e : 0.f;
+        acc[d] = 0.f;
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < L; k0 += 128) {
+        __syncthreads();
+        {
+            const int kr = k0 + threadIdx.x;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                sK[threadIdx.x][d] = kr < L ? __bfloat162float(base[(size_t)kr * rs + C + d]) : 0.f;
+                sV[threadIdx.x][d] = kr < L ? __bfloat162float(base[(size_t)kr * rs + 2 * C + d]) : 0.f;
+            }
+        }
+        __syncthreads();
+        const int kn = min(128, L - k0);
+        for (int kb = 0; kb < kn; kb += 8) {
+            float s[8];
+            float mx = m;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) a = fmaf(q[d], sK[kb + j][d], a);
+                s[j] = (kb + j) < kn ? a : -INFINITY;
+                mx = fmaxf(mx, s[j]);
+            }
+            const float corr = ex2_approx(m - mx);
+            m = mx;
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < D; ++d) acc[d] *= corr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float p = ex2_approx(s[j] - mx);
+                l += p;
+#pragma unroll
+                for (int d = 0; d < D; ++d) acc[d] = fmaf(p, sV[(kb + j) & 127][d], acc[d]);
+            }
+        }
+    }
+    if (qi < L) {
+        const float inv = 1.0f / l;
+        bf16* op = o + ((size_t)b * L + qi) * C + (size_t)head * D;
+#pragma unroll
+        for (int d = 0; d < D; ++d) op[d] = __float2bfloat16(acc[d] * inv);
+    }
+}
+
+inline int flash_attn_init_attrs() {
+    B2D_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  fa_smem_bytes<128>()));
+    B2D_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  fa_smem_bytes<64>()));
+    return 0;
+}
+
+inline int flash_attn_launch(const bf16* qkv, bf16* o, int B, int L, int C, int heads, cudaStream_t st) {
+    B2D_CHECK(C % heads == 0, "attention: C must be divisible by n_heads");
+    const int D = C / heads;
+    const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+    dim3 grid((L + FA_BQ - 1) / FA_BQ, heads, B);
+    switch (D) {
+        case 2: attn_small_d_kernel<2><<<dim3((L + 127) / 128, heads, B), 128, 0, st>>>(qkv, o, L, C, scale_log2e); break;
+        case 4: attn_small_d_kernel<4><<<dim3((L + 127) / 128, heads, B), 128, 0, st>>>(qkv, o, L, C, scale_log2e); break;
+        case 8: attn_small_d_kernel<8><<<dim3((L + 127) / 128, heads, B), 128, 0, st>>>(qkv, o, L, C, scale_log2e); break;
+        case 16: flash_attn_kernel<16><<<grid, 128, fa_smem_bytes<16>(), st>>>(qkv, o, L, C, scale_log2e); break;
+        case 32: flash_attn_kernel<32><<<grid, 128, fa_smem_bytes<32>(), st>>>(qkv, o, L, C, scale_log2e); break;
+        case 64: flash_attn_kernel<64><<<grid, 128, fa_smem_bytes<64>(), st>>>(qkv, o, L, C, scale_log2e); break;
+        case 128: flash_attn_kernel<128><<<grid, 128, fa_smem_bytes<128>(), st>>>(qkv, o, L, C, scale_log2e); break;
+        default: return fail(-1, "attention: unsupported head_dim " + std::to_string(D));
+    }
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b2d

@@ -1,0 +1,919 @@
+// b200ddpm: C-ABI implementation (include/b200ddpm.h) — handle, weight re-packing, the per-step kernel program for
+// Family R (DiffusionNet) and the CUDA-graph sampling loop.  Host orchestration only; all arithmetic is in the kernels.
+#include "../../include/b200ddpm.h"
+
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "conv.cuh"
+#include "elementwise.cuh"
+
+namespace b2d {
+thread_local Status g_status;
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+struct HostTensor {
+    std::vector<float> v;
+    std::vector<int64_t> shape;
+    size_t numel() const { return v.size(); }
+};
+
+static inline uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+typedef std::function<int(cudaStream_t)> Op;
+
+struct Handle {
+    b2d_config cfg{};
+    int num_sms = 148;
+    std::vector<void*> allocs;       // live for the life of the handle
+    std::vector<void*> prog_allocs;  // activations/workspaces of the current per-batch program
+    bool in_prog = false;
+    std::map<std::string, HostTensor> sd;
+    std::map<std::string, void*> dev;  // packed device weights by role name
+    bool weights_loaded = false;
+
+    // schedule
+    int T = 0;
+    float *d_betas = nullptr, *d_alphas = nullptr, *d_alpha_hat = nullptr;
+
+    // per-batch program
+    int prog_B = 0;
+    std::vector<Op> step_ops;    // one eps evaluation (reads cur_x, writes cur_eps)
+    size_t stats_floats = 0;
+    float* d_stats = nullptr;
+    const float* cur_x = nullptr;
+    float* cur_eps = nullptr;
+    float* d_eps = nullptr;  // internal eps buffer for sampling
+    int *d_t = nullptr, *d_step = nullptr, *d_y = nullptr;
+    bool has_y = false, has_cond_set = false;
+    float* d_cond_stack = nullptr;  // [B][Ccond][H][H] fp32 (lsm, topo, cond...)
+    float* d_cond_pre = nullptr;    // [B][H/2][H/2][64] fp32 : conv1 contribution of the conditioning channels
+    float* d_temb = nullptr;        // [B][n_temb]
+    int n_temb = 0;
+    float* d_x_stage = nullptr;  // device staging for the host entry point
+    float* d_noise_stage = nullptr;
+    size_t noise_stage_elems = 0;
+
+    // sampling graph cache
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey {
+        int B = 0;
+        const void *x = nullptr, *noise = nullptr;
+        uint64_t seed = 0, off = 0;
+        float scale = 0;
+        bool operator==(const GraphKey& o) const {
+            return B == o.B && x == o.x && noise == o.noise && seed == o.seed && off == o.off && scale == o.scale;
+        }
+    } graph_key;
+    int graph_nodes = 0;
+    int64_t last_launches = 0;
+    cudaStream_t own_stream = nullptr;
+    struct Tap { const bf16* p; int C, hw; };
+    std::map<std::string, Tap> taps;  // named activations (NHWC bf16) readable through b2d_debug_read
+
+    template <typename T>
+    int alloc(T** p, size_t count) {
+        void* q = nullptr;
+        B2D_CUDA(cudaMalloc(&q, count * sizeof(T) + 256));
+        (in_prog ? prog_allocs : allocs).push_back(q);
+        *p = reinterpret_cast<T*>(q);
+        return 0;
+    }
+    void free_program() {
+        for (void* p : prog_allocs) cudaFree(p);
+        prog_allocs.clear();
+        step_ops.clear();
+        taps.clear();
+        prog_B = 0;
+    }
+    ~Handle() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        free_program();
+        for (void* p : allocs) cudaFree(p);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ weight packing
+static const HostTensor* find(Handle* h, const std::string& k) {
+    auto it = h->sd.find(k);
+    return it == h->sd.end() ? nullptr : &it->second;
+}
+
+#define NEED(var, key)                                             \
+    const HostTensor* var = find(h, key);                          \
+    if (!var) return fail(-3, std::string("missing tensor ") + (key));
+
+static int upload_f32(Handle* h, const std::string& role, const std::vector<float>& v) {
+    float* d;
+    B2D_TRY(h->alloc(&d, v.size()));
+    B2D_CUDA(cudaMemcpy(d, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    h->dev[role] = d;
+    return 0;
+}
+static int upload_bf16(Handle* h, const std::string& role, const std::vector<uint16_t>& v) {
+    bf16* d;
+    B2D_TRY(h->alloc(&d, v.size()));
+    B2D_CUDA(cudaMemcpy(d, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
+    h->dev[role] = d;
+    return 0;
+}
+
+// Conv2d weight [Cout][Cin][R][S] (+ optional eval-BatchNorm folding) -> bf16 [Cout][(r*S+s)*Cin+ci], fp32 bias.
+// BN fold: s = gamma/sqrt(running_var+1e-5); W' = W*s[co]; b' = beta - running_mean*s (+ conv bias*s).
+static int pack_conv(Handle* h, const std::string& role, const std::string& wkey, const std::string& bias_key,
+                     const std::string& bn_prefix) {
+    NEED(w, wkey);
+    if (w->shape.size() != 4) return fail(-3, wkey + ": expected 4-d weight");
+    const int Cout = (int)w->shape[0], Cin = (int)w->shape[1], R = (int)w->shape[2], S = (int)w->shape[3];
+    std::vector<float> scale(Cout, 1.0f), bias(Cout, 0.0f);
+    if (!bias_key.empty()) {
+        NEED(b, bias_key);
+        for (int i = 0; i < Cout; ++i) bias[i] = b->v[i];
+    }
+    if (!bn_prefix.empty()) {
+        NEED(g, bn_prefix + ".weight");
+        NEED(be, bn_prefix + ".bias");
+        NEED(mu, bn_prefix + ".running_mean");
+        NEED(var, bn_prefix + ".running_var");
+        for (int i = 0; i < Cout; ++i) {
+            const float s = g->v[i] / std::sqrt(var->v[i] + 1e-5f);
+            scale[i] = s;
+            bias[i] = be->v[i] + (bias[i] - mu->v[i]) * s;
+        }
+    }
+    std::vector<uint16_t> p((size_t)Cout * R * S * Cin);
+    for (int co = 0; co < Cout; ++co)
+        for (int ci = 0; ci < Cin; ++ci)
+            for (int r = 0; r < R; ++r)
+                for (int s = 0; s < S; ++s)
+                    p[((size_t)co * R * S + (r * S + s)) * Cin + ci] =
+                        f2bf(w->v[(((size_t)co * Cin + ci) * R + r) * S + s] * scale[co]);
+    B2D_TRY(upload_bf16(h, role + ".w", p));
+    B2D_TRY(upload_f32(h, role + ".b", bias));
+    return 0;
+}
+// ConvTranspose2d weight [Cin][Cout][2][2] -> bf16 [(a*2+b)*Cout+co][ci]; bias [Cout].
+static int pack_convt(Handle* h, const std::string& role, const std::string& prefix) {
+    NEED(w, prefix + ".weight");
+    NEED(b, prefix + ".bias");
+    const int Cin = (int)w->shape[0], Cout = (int)w->shape[1];
+    if (w->shape[2] != 2 || w->shape[3] != 2) return fail(-3, prefix + ": ConvTranspose2d must be k=2");
+    std::vector<uint16_t> p((size_t)4 * Cout * Cin);
+    for (int ci = 0; ci < Cin; ++ci)
+        for (int co = 0; co < Cout; ++co)
+            for (int a = 0; a < 2; ++a)
+                for (int bb = 0; bb < 2; ++bb)
+                    p[((size_t)(a * 2 + bb) * Cout + co) * Cin + ci] = f2bf(w->v[(((size_t)ci * Cout + co) * 2 + a) * 2 + bb]);
+    B2D_TRY(upload_bf16(h, role + ".w", p));
+    B2D_TRY(upload_f32(h, role + ".b", b->v));
+    return 0;
+}
+static int pack_linear(Handle* h, const std::string& role, const std::string& wkey, const std::string& bkey) {
+    NEED(w, wkey);
+    NEED(b, bkey);
+    std::vector<uint16_t> p(w->numel());
+    for (size_t i = 0; i < p.size(); ++i) p[i] = f2bf(w->v[i]);
+    B2D_TRY(upload_bf16(h, role + ".w", p));
+    B2D_TRY(upload_f32(h, role + ".b", b->v));
+    return 0;
+}
+static int pack_attention(Handle* h, const std::string& role, const std::string& prefix, const char* ln, const char* mha) {
+    NEED(g, prefix + "." + ln + ".weight");
+    NEED(b, prefix + "." + ln + ".bias");
+    B2D_TRY(upload_f32(h, role + ".ln.g", g->v));
+    B2D_TRY(upload_f32(h, role + ".ln.b", b->v));
+    B2D_TRY(pack_linear(h, role + ".qkv", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias"));
+    B2D_TRY(pack_linear(h, role + ".out", prefix + "." + mha + ".out_proj.weight", prefix + "." + mha + ".out_proj.bias"));
+    if (h->cfg.attn_ff) {
+        NEED(g2, prefix + ".ff_self.0.weight");
+        NEED(b2, prefix + ".ff_self.0.bias");
+        B2D_TRY(upload_f32(h, role + ".ffln.g", g2->v));
+        B2D_TRY(upload_f32(h, role + ".ffln.b", b2->v));
+        B2D_TRY(pack_linear(h, role + ".ff1", prefix + ".ff_self.1.weight", prefix + ".ff_self.1.bias"));
+        B2D_TRY(pack_linear(h, role + ".ff2", prefix + ".ff_self.3.weight", prefix + ".ff_self.3.bias"));
+    }
+    return 0;
+}
+
+static const int ENC_CH[5] = {64, 64, 128, 256, 512};
+static const int DEC_IN[4] = {512, 256, 128, 64};
+static const int DEC_OUT[4] = {256, 128, 64, 64};
+static const int TEMB_ENC_OFF[5] = {0, 64, 128, 256, 512};
+static const int TEMB_DEC_OFF[4] = {1024, 1280, 1408, 1472};
+static const int TEMB_R_TOTAL = 1536;
+
+static int pack_family_r(Handle* h) {
+    const std::string E = "encoder.", D = "decoder.";
+    {   // stem: fp32 [64][Cin_total][8][8]
+        NEED(w, E + "conv1.weight");
+        const int cin_total = h->cfg.c_hr + h->cfg.has_lsm + h->cfg.has_topo + h->cfg.cond_channels;
+        if (w->shape[0] != 64 || w->shape[1] != cin_total || w->shape[2] != 8 || w->shape[3] != 8)
+            return fail(-3, "encoder.conv1.weight shape does not match the configured input channels");
+        B2D_TRY(upload_f32(h, "stem.w", w->v));
+    }
+    B2D_TRY(pack_conv(h, "conv2", E + "conv2.weight", "", E + "bn1"));
+    for (int li = 1; li <= 4; ++li)
+        for (int bi = 0; bi < 2; ++bi) {
+            const std::string p = E + "layer" + std::to_string(li) + "." + std::to_string(bi) + ".";
+            const std::string r = "l" + std::to_string(li) + "b" + std::to_string(bi);
+            B2D_TRY(pack_conv(h, r + ".c1", p + "conv1.weight", "", p + "bn1"));
+            B2D_TRY(pack_conv(h, r + ".c2", p + "conv2.weight", "", p + "bn2"));
+            if (li > 1 && bi == 0) B2D_TRY(pack_conv(h, r + ".ds", p + "downsample.0.weight", "", p + "downsample.1"));
+        }
+    // time projections: one [1536][256] fp32 matrix (5 encoder + 4 decoder blocks), consumed by temb_project_kernel
+    std::vector<float> W((size_t)TEMB_R_TOTAL * 256), Bv(TEMB_R_TOTAL);
+    for (int i = 0; i < 5; ++i) {
+        NEED(w, E + "time_projection_layers." + std::to_string(i) + ".1.weight");
+        NEED(b, E + "time_projection_layers." + std::to_string(i) + ".1.bias");
+        memcpy(&W[(size_t)TEMB_ENC_OFF[i] * 256], w->v.data(), w->v.size() * 4);
+        memcpy(&Bv[TEMB_ENC_OFF[i]], b->v.data(), b->v.size() * 4);
+    }
+    for (int i = 0; i < 4; ++i) {
+        NEED(w, D + "residual_layers." + std::to_string(i) + ".time_projection_layer.1.weight");
+        NEED(b, D + "residual_layers." + std::to_string(i) + ".time_projection_layer.1.bias");
+        memcpy(&W[(size_t)TEMB_DEC_OFF[i] * 256], w->v.data(), w->v.size() * 4);
+        memcpy(&Bv[TEMB_DEC_OFF[i]], b->v.data(), b->v.size() * 4);
+    }
+    B2D_TRY(upload_f32(h, "temb.w", W));
+    B2D_TRY(upload_f32(h, "temb.b", Bv));
+    if (h->cfg.num_classes > 0) {
+        NEED(le, E + "label_emb.weight");
+        B2D_TRY(upload_f32(h, "label_emb", le->v));
+    }
+    // frequency tables (double pow, rounded once — within 1 ulp of torch's fp32 pow)
+    std::vector<float> enc_inv(128), dec_div(128);
+    for (int j = 0; j < 128; ++j) {
+        enc_inv[j] = (float)(1.0 / (double)(float)std::pow(1000.0, (double)(float)((float)(2 * j) / 256.0f)));
+        dec_div[j] = (float)std::pow(10000.0, (2.0 * j) / 256.0);
+    }
+    B2D_TRY(upload_f32(h, "enc_inv", enc_inv));
+    B2D_TRY(upload_f32(h, "dec_div", dec_div));
+    for (int i = 0; i < 5; ++i)
+        B2D_TRY(pack_attention(h, "ea" + std::to_string(i), E + "attention_layers." + std::to_string(i), "layernorm",
+                               "attention"));
+    for (int i = 0; i < 4; ++i) {
+        const std::string p = D + "residual_layers." + std::to_string(i);
+        B2D_TRY(pack_attention(h, "da" + std::to_string(i), p + ".attention", "layernorm", "attention"));
+        B2D_TRY(pack_convt(h, "d" + std::to_string(i) + ".up", p + ".transpose"));
+        B2D_TRY(pack_conv(h, "d" + std::to_string(i) + ".conv", p + ".conv.weight", p + ".conv.bias", ""));
+    }
+    B2D_TRY(pack_convt(h, "final.up", D + "final_layer.transpose"));
+    {
+        NEED(w, D + "final_layer.conv.weight");
+        NEED(b, D + "final_layer.conv.bias");
+        if (w->shape[0] != h->cfg.c_out || w->shape[1] != 64) return fail(-3, "final_layer.conv.weight shape mismatch");
+        B2D_TRY(upload_f32(h, "tail.w", w->v));
+        B2D_TRY(upload_f32(h, "tail.b", b->v));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ program building
+struct Builder {
+    Handle* h;
+    int B;
+    int err = 0;
+    std::vector<Op>& ops;
+    Builder(Handle* hh, int b, std::vector<Op>& o) : h(hh), B(b), ops(o) {}
+
+    bf16* act(size_t elems) {
+        bf16* p = nullptr;
+        if (h->alloc(&p, elems) != 0) err = -2;
+        return p;
+    }
+    template <typename T>
+    T* W(const std::string& role) {
+        auto it = h->dev.find(role);
+        if (it == h->dev.end()) {
+            err = fail(-3, "internal: missing packed weight " + role);
+            return nullptr;
+        }
+        return reinterpret_cast<T*>(it->second);
+    }
+
+    // GEMM-shaped op through the tcgen05 kernel (or the SIMT cross-check when cfg.debug_simt_conv)
+    void conv(const bf16* in, int Hi, int Wi, int Cin, bf16* out, int Cout, int R, int stride, int pad, bool convt,
+              const std::string& role, const bf16* residual, const float* post_add, int post_stride, int act) {
+        auto pl = std::make_shared<ConvPlan>();
+        ConvParams& p = pl->p;
+        memset(&p, 0, sizeof(p));
+        p.B = B; p.Hi = Hi; p.Wi = Wi; p.Cin = Cin;
+        p.R = R; p.S = R; p.stride = stride; p.pad = pad;
+        p.convt = convt ? 1 : 0;
+        if (convt) {
+            p.Ho = Hi; p.Wo = Wi; p.Cout = 4 * Cout; p.CoutT = Cout;
+        } else {
+            p.Ho = (Hi + 2 * pad - R) / stride + 1;
+            p.Wo = (Wi + 2 * pad - R) / stride + 1;
+            p.Cout = Cout; p.CoutT = Cout;
+        }
+        p.in = in;
+        p.w = W<bf16>(role + ".w");
+        p.bias = W<float>(role + ".b");
+        p.residual = residual;
+        p.post_add = post_add;
+        p.post_stride = post_stride;
+        p.act = act;
+        p.out = out;
+        if (err) return;
+        if (h->cfg.debug_simt_conv) {
+            ops.push_back([pl](cudaStream_t st) { return conv_launch_simt(pl->p, st); });
+        } else {
+            if (conv_plan_build(*pl, h->num_sms) != 0) { err = -1; return; }
+            ops.push_back([pl](cudaStream_t st) { return conv_launch_tc(*pl, st); });
+        }
+    }
+
+    // scratch shared by all attention blocks (they run one after another)
+    bf16 *s_xn = nullptr, *s_qkv = nullptr, *s_ao = nullptr, *s_h1 = nullptr, *s_mid = nullptr;
+
+    // ImageSelfAttention (+ optional FF tail) on tokens x [B, hw*hw, C]; final_act applies to the block output.
+    void attention(const bf16* x, int hw, int C, const std::string& role, bf16* out, int final_act) {
+        const int rows = B * hw * hw, L = hw * hw, heads = h->cfg.n_heads;
+        const float* g = W<float>(role + ".ln.g");
+        const float* b = W<float>(role + ".ln.b");
+        bf16 *xn = s_xn, *qkv = s_qkv, *ao = s_ao;
+        const int Bc = B;
+        ops.push_back([=](cudaStream_t st) { return layernorm_launch(x, g, b, xn, rows, C, st); });
+        conv(xn, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkv", nullptr, nullptr, 0, 0);
+        ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
+        if (!h->cfg.attn_ff) {
+            conv(ao, hw, hw, C, out, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, final_act);
+        } else {
+            bf16* mid = s_mid;
+            bf16* h1 = s_h1;
+            conv(ao, hw, hw, C, mid, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, 0);
+            const float* g2 = W<float>(role + ".ffln.g");
+            const float* b2 = W<float>(role + ".ffln.b");
+            ops.push_back([=](cudaStream_t st) { return layernorm_launch(mid, g2, b2, xn, rows, C, st); });
+            conv(xn, hw, hw, C, h1, C, 1, 1, 0, false, role + ".ff1", nullptr, nullptr, 0, 2);
+            conv(h1, hw, hw, C, out, C, 1, 1, 0, false, role + ".ff2", mid, nullptr, 0, final_act);
+        }
+    }
+
+    float* stats_slice(int C) {
+        float* p = h->d_stats + h->stats_floats;
+        h->stats_floats += (size_t)B * C * 2;
+        return p;
+    }
+    void plane_stats(const bf16* x, int hw, int C, float* st) {
+        const int HW = hw * hw, Bc = B;
+        int ppc = 256;  // pixels per CTA
+        ops.push_back([=](cudaStream_t s) {
+            dim3 grid((HW + ppc - 1) / ppc, C / 64, Bc);
+            plane_stats_kernel<<<grid, 256, 0, s>>>(x, st, HW, C, ppc);
+            B2D_CUDA(cudaGetLastError());
+            return 0;
+        });
+    }
+    void instnorm_apply(const bf16* x, const float* st, const bf16* skip, const float* vec, int vec_stride, bf16* y, int hw,
+                        int C) {
+        const int HW = hw * hw;
+        const size_t total8 = (size_t)B * HW * C / 8;
+        ops.push_back([=](cudaStream_t s) {
+            int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
+            instnorm_apply_kernel<<<blocks, 256, 0, s>>>(x, st, skip, vec, vec_stride, y, HW, C, total8);
+            B2D_CUDA(cudaGetLastError());
+            return 0;
+        });
+    }
+};
+
+}  // namespace b2d
+#include "family_d.cuh"
+namespace b2d {
+
+static const size_t STATS_CAPACITY_PER_SAMPLE = 2 * (512 + 256 + 256 + 128 + 128 + 64 + 64 + 64 + 64) + 4096;
+
+static int build_program_r(Handle* h, int B) {
+    const b2d_config& c = h->cfg;
+    const int H = c.img_size;
+    const int s[6] = {H, H / 2, H / 4, H / 8, H / 16, H / 32};
+    std::vector<Op> ops;
+    Builder bd(h, B, ops);
+    h->stats_floats = 0;
+    // scratch for attention (largest layer: fmap1 / dec3, rows = B*s1^2, C = 64; deeper layers are never larger)
+    size_t max_rc = 0;
+    for (int i = 0; i < 5; ++i) max_rc = std::max(max_rc, (size_t)B * s[i + 1] * s[i + 1] * ENC_CH[i]);
+    bd.s_xn = bd.act(max_rc);
+    bd.s_qkv = bd.act(max_rc * 3);
+    bd.s_ao = bd.act(max_rc);
+    if (c.attn_ff) {
+        bd.s_h1 = bd.act(max_rc);
+        bd.s_mid = bd.act(max_rc);
+    }
+    float* temb = h->d_temb;
+    const int TS = TEMB_R_TOTAL;
+
+    // ---- time embeddings + all nine projections (one launch)
+    {
+        Handle* hh = h;
+        const float* label = c.num_classes > 0 ? bd.W<float>("label_emb") : nullptr;
+        const float* ei = bd.W<float>("enc_inv");
+        const float* dd = bd.W<float>("dec_div");
+        const float* tw = bd.W<float>("temb.w");
+        const float* tb = bd.W<float>("temb.b");
+        ops.push_back([=](cudaStream_t st) {
+            temb_project_kernel<<<B, 256, 0, st>>>(hh->d_t, hh->has_y ? hh->d_y : nullptr, label, ei, dd, tw, tb, temb, 1024,
+                                                   TS);
+            B2D_CUDA(cudaGetLastError());
+            return 0;
+        });
+    }
+    // ---- Encoder.forward (modules_DANRA_conditional.py:213-312)
+    bf16* f1_pre = bd.act((size_t)B * s[1] * s[1] * 64);
+    {
+        Handle* hh = h;
+        const float* sw = bd.W<float>("stem.w");
+        const int cin_total = c.c_hr + c.has_lsm + c.has_topo + c.cond_channels;
+        const int chr = c.c_hr, Hh = H, ho = s[1];
+        ops.push_back([=](cudaStream_t st) {
+            dim3 grid(ho / 8, ho / 8, B);
+            const bool have_cond = (cin_total > chr);
+            stem_conv_kernel<8, 2><<<grid, 256, 0, st>>>(hh->cur_x, chr, Hh, Hh, sw, cin_total, 0,
+                                                         have_cond ? hh->d_cond_pre : nullptr, temb + TEMB_ENC_OFF[0], TS,
+                                                         f1_pre, nullptr, ho, ho, 3);
+            B2D_CUDA(cudaGetLastError());
+            return 0;
+        });
+    }
+    bf16* fmap[5];
+    fmap[0] = bd.act((size_t)B * s[1] * s[1] * 64);
+    bd.attention(f1_pre, s[1], 64, "ea0", fmap[0], 0);
+    h->taps["f1_pre"] = {f1_pre, 64, s[1]};
+    h->taps["fmap1"] = {fmap[0], 64, s[1]};
+    // conv2 -> bn1 -> relu (:269-273)
+    bf16* cur = bd.act((size_t)B * s[2] * s[2] * 64);
+    bd.conv(fmap[0], s[1], s[1], 64, cur, 64, 8, 2, 3, false, "conv2", nullptr, nullptr, 0, 1);
+    int cin = 64;
+    for (int li = 1; li <= 4; ++li) {
+        const int cout = ENC_CH[li];
+        const int hin = (li == 1) ? s[2] : s[li];  // input extent of this layer
+        const int hout = s[li + 1];
+        const size_t n_out = (size_t)B * hout * hout * cout;
+        const std::string r0 = "l" + std::to_string(li) + "b0", r1 = "l" + std::to_string(li) + "b1";
+        bf16* t1 = bd.act(n_out);
+        bf16* b0 = bd.act(n_out);
+        bf16* pre = bd.act(n_out);
+        const bf16* identity = cur;
+        const int stride = (li > 1) ? 2 : 1;
+        bd.conv(cur, hin, hin, cin, t1, cout, 3, stride, 1, false, r0 + ".c1", nullptr, nullptr, 0, 1);
+        if (li > 1) {
+            bf16* ds = bd.act(n_out);
+            bd.conv(cur, hin, hin, cin, ds, cout, 1, 2, 0, false, r0 + ".ds", nullptr, nullptr, 0, 0);
+            identity = ds;
+        }
+        bd.conv(t1, hout, hout, cout, b0, cout, 3, 1, 1, false, r0 + ".c2", identity, nullptr, 0, 1);
+        bd.conv(b0, hout, hout, cout, t1, cout, 3, 1, 1, false, r1 + ".c1", nullptr, nullptr, 0, 1);
+        // last conv of the stage: + identity, ReLU, then + time projection (fmap = layer(x) + t_emb, :276-280)
+        bd.conv(t1, hout, hout, cout, pre, cout, 3, 1, 1, false, r1 + ".c2", b0, temb + TEMB_ENC_OFF[li], TS, 1);
+        fmap[li] = bd.act(n_out);
+        bd.attention(pre, hout, cout, "ea" + std::to_string(li), fmap[li], 0);
+        h->taps["pre" + std::to_string(li + 1)] = {pre, cout, hout};
+        h->taps["fmap" + std::to_string(li + 1)] = {fmap[li], cout, hout};
+        cur = fmap[li];
+        cin = cout;
+    }
+    // ---- Decoder.forward (:512-536), DecoderBlock.forward (:425-460)
+    const bf16* dcur = fmap[4];
+    for (int i = 0; i < 4; ++i) {
+        const int ci = DEC_IN[i], co = DEC_OUT[i];
+        const int hin = s[5 - i], hout = s[4 - i];
+        const std::string r = "d" + std::to_string(i);
+        bf16* up = bd.act((size_t)B * hout * hout * ci);
+        bd.conv(dcur, hin, hin, ci, up, ci, 1, 1, 0, true, r + ".up", nullptr, nullptr, 0, 0);
+        float* st1 = bd.stats_slice(ci);
+        bd.plane_stats(up, hout, ci, st1);
+        bd.instnorm_apply(up, st1, nullptr, nullptr, 0, up, hout, ci);
+        bf16* cv = bd.act((size_t)B * hout * hout * co);
+        bd.conv(up, hout, hout, ci, cv, co, 3, 1, 1, false, r + ".conv", nullptr, nullptr, 0, 0);
+        float* st2 = bd.stats_slice(co);
+        bd.plane_stats(cv, hout, co, st2);
+        bf16* pre = bd.act((size_t)B * hout * hout * co);
+        bd.instnorm_apply(cv, st2, fmap[3 - i], temb + TEMB_DEC_OFF[i], TS, pre, hout, co);
+        bf16* dout = bd.act((size_t)B * hout * hout * co);
+        bd.attention(pre, hout, co, "da" + std::to_string(i), dout, 1 /*ReLU after attention, :459*/);
+        h->taps["dec" + std::to_string(i) + "_pre"] = {pre, co, hout};
+        h->taps["dec" + std::to_string(i)] = {dout, co, hout};
+        dcur = dout;
+    }
+    // ---- final_layer: ConvT -> IN -> Conv3x3(64->c_out), no skip/time/attention/activation (:503-509, :535)
+    {
+        bf16* up = bd.act((size_t)B * H * H * 64);
+        bd.conv(dcur, s[1], s[1], 64, up, 64, 1, 1, 0, true, "final.up", nullptr, nullptr, 0, 0);
+        float* st = bd.stats_slice(64);
+        bd.plane_stats(up, H, 64, st);
+        Handle* hh = h;
+        const float* tw = bd.W<float>("tail.w");
+        const float* tb = bd.W<float>("tail.b");
+        const int cout = c.c_out, Hh = H;
+        ops.push_back([=](cudaStream_t s2) {
+            dim3 grid((Hh + 31) / 32, (Hh + 7) / 8, B);
+            tail_conv_kernel<<<grid, 256, 0, s2>>>(up, st, tw, tb, hh->cur_eps, Hh, Hh, cout);
+            B2D_CUDA(cudaGetLastError());
+            return 0;
+        });
+    }
+    if (bd.err) return g_status.code ? g_status.code : fail(-1, "program build failed");
+    if (h->stats_floats > STATS_CAPACITY_PER_SAMPLE * (size_t)c.max_batch) return fail(-1, "internal: stats buffer too small");
+    h->step_ops.swap(ops);
+    h->prog_B = B;
+    return 0;
+}
+
+static int ensure_program(Handle* h, int B) {
+    B2D_CHECK(h->weights_loaded, "b2d_load_weights has not been called");
+    B2D_CHECK(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch of the handle");
+    if (h->prog_B == B) return 0;
+    if (h->graph_exec) {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    h->free_program();
+    h->in_prog = true;
+    const int rc = (h->cfg.family == B2D_FAMILY_R) ? build_program_r(h, B) : build_program_d(h, B);
+    h->in_prog = false;
+    if (rc) h->free_program();
+    return rc;
+}
+
+static int run_step_ops(Handle* h, cudaStream_t st) {
+    if (h->stats_floats) B2D_CUDA(cudaMemsetAsync(h->d_stats, 0, h->stats_floats * sizeof(float), st));
+    for (auto& op : h->step_ops) B2D_TRY(op(st));
+    return 0;
+}
+
+}  // namespace b2d
+
+using namespace b2d;
+struct b2d_handle : public b2d::Handle {};
+
+// ================================================================================================= C ABI
+extern "C" {
+
+const char* b2d_last_error(void) { return g_status.msg.c_str(); }
+int b2d_abi_version(void) { return B2D_ABI_VERSION; }
+
+int b2d_create(const b2d_config* cfg, b2d_handle** out) {
+    B2D_CHECK(cfg && out, "null argument");
+    B2D_CHECK(cfg->family == B2D_FAMILY_R || cfg->family == B2D_FAMILY_D, "unknown family");
+    B2D_CHECK(is_pow2(cfg->img_size) && cfg->img_size >= 32 && cfg->img_size <= 128, "img_size must be 32, 64 or 128");
+    B2D_CHECK(cfg->max_batch >= 1, "max_batch must be positive");
+    B2D_CHECK(cfg->c_hr >= 1 && cfg->c_out >= 1, "channel counts must be positive");
+    int dev = 0, ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(-2, "no CUDA device: this library has no CPU fallback (" + std::string(cudaGetErrorString(e)) + ")");
+    B2D_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    B2D_CUDA(cudaGetDeviceProperties(&prop, dev));
+    B2D_CHECK(prop.major == 10, "b200ddpm kernels are compiled for sm_100a only");
+    auto* h = new b2d_handle();
+    h->cfg = *cfg;
+    if (h->cfg.n_heads <= 0) h->cfg.n_heads = 4;
+    h->num_sms = prop.multiProcessorCount;
+    int rc = 0;
+    do {
+        if ((rc = conv_tc_init_attrs())) break;
+        if ((rc = flash_attn_init_attrs())) break;
+        const int B = cfg->max_batch, H = cfg->img_size;
+        const size_t n = (size_t)B * cfg->c_hr * H * H;
+        if ((rc = h->alloc(&h->d_t, B))) break;
+        if ((rc = h->alloc(&h->d_y, B))) break;
+        if ((rc = h->alloc(&h->d_step, 4))) break;
+        if ((rc = h->alloc(&h->d_eps, (size_t)B * cfg->c_out * H * H))) break;
+        if ((rc = h->alloc(&h->d_x_stage, n))) break;
+        if ((rc = h->alloc(&h->d_stats, STATS_CAPACITY_PER_SAMPLE * (size_t)B))) break;
+        h->n_temb = TEMB_R_TOTAL;
+        if ((rc = h->alloc(&h->d_temb, (size_t)B * 2048))) break;
+        const int ccond = cfg->has_lsm + cfg->has_topo + cfg->cond_channels;
+        if ((rc = h->alloc(&h->d_cond_stack, (size_t)B * std::max(ccond, 1) * H * H))) break;
+        if ((rc = h->alloc(&h->d_cond_pre, (size_t)B * (H / 2) * (H / 2) * 64))) break;
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "stream create failed"); break; }
+    } while (0);
+    if (rc) {
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+void b2d_destroy(b2d_handle* h) { delete h; }
+
+int b2d_load_weights(b2d_handle* h, const b2d_tensor* tensors, int32_t n) {
+    B2D_CHECK(h && tensors && n > 0, "null argument");
+    B2D_CHECK(!h->weights_loaded, "weights already loaded on this handle (create a new handle to reload)");
+    h->sd.clear();
+    for (int i = 0; i < n; ++i) {
+        const b2d_tensor& t = tensors[i];
+        B2D_CHECK(t.name && t.data && t.ndim >= 0 && t.ndim <= 4, "malformed tensor entry");
+        HostTensor ht;
+        size_t numel = 1;
+        for (int d = 0; d < t.ndim; ++d) {
+            ht.shape.push_back(t.shape[d]);
+            numel *= (size_t)t.shape[d];
+        }
+        ht.v.assign(t.data, t.data + numel);
+        h->sd[t.name] = std::move(ht);
+    }
+    int rc = (h->cfg.family == B2D_FAMILY_R) ? pack_family_r(h) : pack_family_d(h);
+    h->sd.clear();
+    if (rc) return rc;
+    h->weights_loaded = true;
+    return 0;
+}
+
+int b2d_set_schedule(b2d_handle* h, const float* betas, const float* alphas, const float* alpha_hat, int32_t T) {
+    B2D_CHECK(h && betas && alphas && alpha_hat && T >= 2, "bad schedule");
+    if (T != h->T) {
+        B2D_TRY(h->alloc(&h->d_betas, T));
+        B2D_TRY(h->alloc(&h->d_alphas, T));
+        B2D_TRY(h->alloc(&h->d_alpha_hat, T));
+        h->T = T;
+    }
+    B2D_CUDA(cudaMemcpy(h->d_betas, betas, T * 4, cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMemcpy(h->d_alphas, alphas, T * 4, cudaMemcpyHostToDevice));
+    B2D_CUDA(cudaMemcpy(h->d_alpha_hat, alpha_hat, T * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, const float* cond, int32_t cond_h,
+                         int32_t cond_w, const int64_t* y, int32_t B, void* stream) {
+    B2D_CHECK(h, "null handle");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = as_stream(stream);
+    const b2d_config& c = h->cfg;
+    const int H = c.img_size;
+    if (y) {
+        B2D_CHECK(c.num_classes > 0, "y given but the model has no label embedding");
+        // int64 -> int32 on device
+        std::vector<int64_t> tmp(B);
+        B2D_CUDA(cudaMemcpyAsync(tmp.data(), y, B * 8, cudaMemcpyDeviceToHost, st));
+        B2D_CUDA(cudaStreamSynchronize(st));
+        std::vector<int> yi(B);
+        for (int i = 0; i < B; ++i) {
+            B2D_CHECK(tmp[i] >= 0 && tmp[i] < c.num_classes, "class label out of range");
+            yi[i] = (int)tmp[i];
+        }
+        B2D_CUDA(cudaMemcpyAsync(h->d_y, yi.data(), B * 4, cudaMemcpyHostToDevice, st));
+        B2D_CUDA(cudaStreamSynchronize(st));
+    }
+    h->has_y = (y != nullptr);
+    if (c.family == B2D_FAMILY_D) return set_conditioning_d(h, cond, cond_h, cond_w, B, st);
+    // Family R: stack [lsm, topo, cond] (concat order of Encoder.forward :228-238) per sample, then conv1's share of it
+    B2D_CHECK(!c.has_lsm || lsm, "model was built with lsm_tensor: lsm_cond is required");
+    B2D_CHECK(!c.has_topo || topo, "model was built with topo_tensor: topo_cond is required");
+    B2D_CHECK((c.cond_channels > 0) == (cond != nullptr), "cond_img presence must match cond_on_img of the model");
+    const int ccond = c.has_lsm + c.has_topo + c.cond_channels;
+    if (ccond == 0) return 0;
+    const size_t plane = (size_t)H * H;
+    int ch = 0;
+    auto put = [&](const float* src, int nch) -> int {
+        B2D_CUDA(cudaMemcpy2DAsync(h->d_cond_stack + (size_t)ch * plane, (size_t)ccond * plane * 4, src, (size_t)nch * plane * 4,
+                                   (size_t)nch * plane * 4, B, cudaMemcpyDeviceToDevice, st));
+        ch += nch;
+        return 0;
+    };
+    if (c.has_lsm) B2D_TRY(put(lsm, 1));
+    if (c.has_topo) B2D_TRY(put(topo, 1));
+    if (c.cond_channels) B2D_TRY(put(cond, c.cond_channels));
+    const int cin_total = c.c_hr + ccond;
+    dim3 grid(H / 2 / 8, H / 2 / 8, B);
+    stem_conv_kernel<8, 2><<<grid, 256, 0, st>>>(h->d_cond_stack, ccond, H, H, reinterpret_cast<float*>(h->dev["stem.w"]),
+                                                 cin_total, c.c_hr, nullptr, nullptr, 0, nullptr, h->d_cond_pre, H / 2, H / 2,
+                                                 3);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps_out, int32_t B, void* stream) {
+    B2D_CHECK(h && x && t_host && eps_out, "null argument");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = as_stream(stream);
+    std::vector<int> ti(B);
+    for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
+    B2D_CUDA(cudaMemcpyAsync(h->d_t, ti.data(), B * 4, cudaMemcpyHostToDevice, st));
+    B2D_CUDA(cudaStreamSynchronize(st));  // ti is a stack-lifetime staging buffer
+    h->cur_x = x;
+    h->cur_eps = eps_out;
+    B2D_TRY(run_step_ops(h, st));
+    h->last_launches = (int64_t)h->step_ops.size() + 1;
+    return 0;
+}
+
+int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed, uint64_t sample_offset,
+               float noise_scale, int32_t B, void* stream) {
+    B2D_CHECK(h && x_inout, "null argument");
+    B2D_CHECK(h->T >= 2, "b2d_set_schedule has not been called");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = as_stream(stream);
+    const b2d_config& c = h->cfg;
+    const size_t per_sample = (size_t)c.c_hr * c.img_size * c.img_size;
+    const size_t n = per_sample * B;
+    B2D_CHECK(c.c_hr == c.c_out, "sampling needs c_out == c_hr");
+    Handle::GraphKey key;
+    key.B = B; key.x = x_inout; key.noise = noise; key.seed = seed; key.off = sample_offset; key.scale = noise_scale;
+    if (!h->graph_exec || !(key == h->graph_key)) {
+        if (h->graph_exec) {
+            cudaGraphExecDestroy(h->graph_exec);
+            h->graph_exec = nullptr;
+        }
+        // capture ONE reverse step; the step index lives in device memory so the same graph serves every i
+        cudaStream_t cs = h->own_stream;
+        h->cur_x = x_inout;
+        h->cur_eps = h->d_eps;
+        B2D_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = run_step_ops(h, cs);
+        if (rc == 0) {
+            const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)h->num_sms * 8);
+            posterior_update_kernel<<<blocks, 256, 0, cs>>>(x_inout, h->d_eps, noise, h->d_alphas, h->d_betas, h->d_alpha_hat,
+                                                            h->d_step, h->d_t, B, n, per_sample, seed, sample_offset,
+                                                            noise_scale);
+            step_advance_kernel<<<1, 256, 0, cs>>>(h->d_step, h->d_t, B);
+            if (cudaGetLastError() != cudaSuccess) rc = fail(-2, "launch failed during graph capture");
+        }
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc) return rc;
+        B2D_CUDA(ce);
+        size_t nn = 0;
+        cudaGraphGetNodes(graph, nullptr, &nn);
+        h->graph_nodes = (int)nn;
+        cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        B2D_CUDA(ie);
+        h->graph_key = key;
+    }
+    const int T = h->T;
+    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(h->d_t, T - 1, B);
+    fill_int_kernel<<<1, 32, 0, st>>>(h->d_step, T - 1, 1);
+    B2D_CUDA(cudaGetLastError());
+    for (int i = T - 1; i >= 1; --i) B2D_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    h->last_launches = (int64_t)h->graph_nodes * (T - 1) + 2;
+    return 0;
+}
+
+int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, const float* topo_host,
+                    const float* cond_host, int32_t cond_h, int32_t cond_w, const int64_t* y_host,
+                    const float* noise_host, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B) {
+    B2D_CHECK(h && x_inout_host, "null argument");
+    B2D_CHECK(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch of the handle");
+    const b2d_config& c = h->cfg;
+    const int H = c.img_size;
+    cudaStream_t st = h->own_stream;
+    const size_t plane = (size_t)H * H;
+    const size_t n = (size_t)B * c.c_hr * plane;
+    B2D_CUDA(cudaMemcpyAsync(h->d_x_stage, x_inout_host, n * 4, cudaMemcpyHostToDevice, st));
+    // conditioning staging (freed with the handle; sized on first use)
+    float *d_lsm = nullptr, *d_topo = nullptr, *d_cond = nullptr;
+    int64_t* d_y = nullptr;
+    std::vector<void*> tmp;
+    auto stage = [&](const void* src, size_t bytes, void** dst) -> int {
+        if (!src) return 0;
+        B2D_CUDA(cudaMalloc(dst, bytes));
+        tmp.push_back(*dst);
+        B2D_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return 0;
+    };
+    int rc = 0;
+    do {
+        if ((rc = stage(lsm_host, (size_t)B * plane * 4, (void**)&d_lsm))) break;
+        if ((rc = stage(topo_host, (size_t)B * plane * 4, (void**)&d_topo))) break;
+        const size_t cond_elems = (c.family == B2D_FAMILY_D) ? (size_t)B * c.cond_channels * cond_h * cond_w
+                                                             : (size_t)B * c.cond_channels * plane;
+        if ((rc = stage(cond_host, cond_elems * 4, (void**)&d_cond))) break;
+        if ((rc = stage(y_host, (size_t)B * 8, (void**)&d_y))) break;
+        if (noise_host) {
+            const size_t ne = (size_t)h->T * n;
+            if (ne > h->noise_stage_elems) {
+                if ((rc = h->alloc(&h->d_noise_stage, ne))) break;
+                h->noise_stage_elems = ne;
+            }
+            if (cudaMemcpyAsync(h->d_noise_stage, noise_host, ne * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+                rc = fail(-2, "noise upload failed");
+                break;
+            }
+        }
+        if ((rc = b2d_set_conditioning(h, d_lsm, d_topo, d_cond, cond_h, cond_w, d_y, B, st))) break;
+        if ((rc = b2d_sample(h, h->d_x_stage, noise_host ? h->d_noise_stage : nullptr, seed, sample_offset, noise_scale, B, st)))
+            break;
+        if (cudaMemcpyAsync(x_inout_host, h->d_x_stage, n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+            rc = fail(-2, "result download failed");
+            break;
+        }
+    } while (0);
+    cudaError_t se = cudaStreamSynchronize(st);
+    for (void* p : tmp) cudaFree(p);
+    if (rc) return rc;
+    B2D_CUDA(se);
+    return 0;
+}
+
+int64_t b2d_last_launch_count(const b2d_handle* h) { return h ? h->last_launches : 0; }
+
+int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out) {
+    B2D_CHECK(h && name && out_host, "null argument");
+    auto it = h->taps.find(name);
+    if (it == h->taps.end()) return fail(-3, std::string("no such tap: ") + name);
+    const size_t n = (size_t)h->prog_B * it->second.hw * it->second.hw * it->second.C;
+    B2D_CHECK((int64_t)n <= max_elems, "output buffer too small");
+    std::vector<uint16_t> tmp(n);
+    B2D_CUDA(cudaDeviceSynchronize());
+    B2D_CUDA(cudaMemcpy(tmp.data(), it->second.p, n * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t u = (uint32_t)tmp[i] << 16;
+        memcpy(&out_host[i], &u, 4);
+    }
+    if (C_out) *C_out = it->second.C;
+    if (hw_out) *hw_out = it->second.hw;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ single operators
+int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* residual, const float* post_add,
+                  int32_t post_stride, void* out, int32_t B, int32_t Hi, int32_t Wi, int32_t Cin, int32_t Cout, int32_t R,
+                  int32_t S, int32_t stride, int32_t pad, int32_t convt, int32_t act, int32_t impl, void* stream) {
+    B2D_CHECK(in && w && out, "null argument");
+    B2D_CHECK(R == S, "square filters only");
+    ConvPlan pl;
+    ConvParams& p = pl.p;
+    memset(&p, 0, sizeof(p));
+    p.B = B; p.Hi = Hi; p.Wi = Wi; p.Cin = Cin; p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.convt = convt;
+    if (convt) {
+        p.Ho = Hi; p.Wo = Wi; p.Cout = 4 * Cout; p.CoutT = Cout;
+    } else {
+        p.Ho = (Hi + 2 * pad - R) / stride + 1;
+        p.Wo = (Wi + 2 * pad - S) / stride + 1;
+        p.Cout = Cout; p.CoutT = Cout;
+    }
+    p.in = (const bf16*)in; p.w = (const bf16*)w; p.bias = bias; p.residual = (const bf16*)residual;
+    p.post_add = post_add; p.post_stride = post_stride; p.act = act; p.out = (bf16*)out;
+    if (impl == 1) return conv_launch_simt(p, as_stream(stream));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    B2D_TRY(conv_tc_init_attrs());
+    B2D_TRY(conv_plan_build(pl, sms));
+    return conv_launch_tc(pl, as_stream(stream));
+}
+
+int b2d_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t C, void* stream) {
+    return layernorm_launch((const bf16*)x, gamma, beta, (bf16*)y, rows, C, as_stream(stream));
+}
+
+int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream) {
+    B2D_TRY(flash_attn_init_attrs());
+    return flash_attn_launch((const bf16*)qkv, (bf16*)o, B, L, C, heads, as_stream(stream));
+}
+
+int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t vec_stride, void* y, float* stats_ws,
+                    int32_t B, int32_t HW, int32_t C, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    B2D_CHECK(C % 64 == 0, "C must be a multiple of 64");
+    B2D_CUDA(cudaMemsetAsync(stats_ws, 0, (size_t)B * C * 2 * sizeof(float), st));
+    dim3 grid((HW + 255) / 256, C / 64, B);
+    plane_stats_kernel<<<grid, 256, 0, st>>>((const bf16*)x, stats_ws, HW, C, 256);
+    const size_t total8 = (size_t)B * HW * C / 8;
+    const int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
+    instnorm_apply_kernel<<<blocks, 256, 0, st>>>((const bf16*)x, stats_ws, (const bf16*)skip, vec, vec_stride, (bf16*)y, HW,
+                                                  C, total8);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_op_posterior_update(float* x, const float* eps, const float* z, const float* betas, const float* alphas,
+                            const float* alpha_hat, int32_t i, int32_t B, int64_t per_sample, uint64_t seed,
+                            uint64_t sample_offset, float noise_scale, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    int* d_step = nullptr;
+    B2D_CUDA(cudaMalloc(&d_step, 16));
+    fill_int_kernel<<<1, 32, 0, st>>>(d_step, i, 1);
+    const size_t n = (size_t)B * per_sample;
+    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)148 * 8);
+    // z (if given) is the noise of THIS step: bias the pointer so that noise + i*n lands on it
+    const float* noise = z ? z - (size_t)i * n : nullptr;
+    posterior_update_kernel<<<blocks, 256, 0, st>>>(x, eps, noise, alphas, betas, alpha_hat, d_step, nullptr, B, n,
+                                                    (size_t)per_sample, seed, sample_offset, noise_scale);
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(st);
+    cudaFree(d_step);
+    B2D_CUDA(e);
+    return 0;
+}
+
+}  // extern "C"

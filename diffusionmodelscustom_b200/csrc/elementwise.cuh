@@ -1,0 +1,350 @@
+// HBM/latency-bound kernels of the sampling step: time embeddings + projections, the 8x8/s2 stem convolution on the
+// fp32 state, InstanceNorm statistics/apply, the Cout=1 tail convolution and the DDPM posterior update.
+#pragma once
+#include "common.cuh"
+
+namespace b2d {
+
+// ------------------------------------------------------------------------------------------------ time embeddings
+// One CTA per sample.  Computes both reference embeddings and all nine SiLU->Linear projections in one launch:
+//   encoder (modules_DANRA_conditional.py:203-211,256): e = [sin(t*inv_j) | cos(t*inv_j)] (+ label_emb[y]), inv_j = 1000^(-2j/256)
+//   decoder (modules_DANRA_conditional.py:42-63):       d[2j] = sin(t/div_j), d[2j+1] = cos(t/div_j),   div_j = 10000^(2j/256)
+//   out[b][o] = bias[o] + sum_k W[o][k] * silu(emb_sel(o)[k]),  rows o < n_enc use e, the rest use d.
+// Family D (unet_ms.py:138-146) uses the [sin|cos] layout with base 10000 for every projection (n_enc = n_out, inv table differs).
+constexpr int TEMB_DIM = 256;
+__global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict__ t, const int* __restrict__ y,
+                                                           const float* __restrict__ label_emb,  // [ncls][256] or null
+                                                           const float* __restrict__ enc_inv,    // [128]
+                                                           const float* __restrict__ dec_div,    // [128]
+                                                           const float* __restrict__ W,          // [n_out][256]
+                                                           const float* __restrict__ bias,       // [n_out]
+                                                           float* __restrict__ out,              // [B][n_out]
+                                                           int n_enc, int n_out) {
+    __shared__ float se[TEMB_DIM], sd[TEMB_DIM];
+    const int b = blockIdx.x;
+    const float tf = (float)t[b];
+    {
+        const int k = threadIdx.x;  // 256 threads <-> 256 embedding entries
+        const int j = k & 127;
+        const float a = tf * enc_inv[j];
+        float e = (k < 128) ? sinf(a) : cosf(a);
+        if (label_emb != nullptr && y != nullptr) e += label_emb[(size_t)y[b] * TEMB_DIM + k];
+        se[k] = silu(e);
+        const float a2 = __fdiv_rn(tf, dec_div[k >> 1]);
+        const float d = (k & 1) ? cosf(a2) : sinf(a2);
+        sd[k] = silu(d);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < n_out; o += 8) {
+        const float* w = W + (size_t)o * TEMB_DIM;
+        const float* e = (o < n_enc) ? se : sd;
+        float acc = 0.f;
+#pragma unroll
+        for (int k = lane; k < TEMB_DIM; k += 32) acc = fmaf(w[k], e[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) out[(size_t)b * n_out + o] = acc + bias[o];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ stem convolution
+// Direct KSxKS / stride / pad convolution of an fp32 NCHW tensor with few channels (the diffusion state x, or the
+// step-invariant conditioning stack) to 64 channels, NHWC output.  FP32 FMA: K = KS*KS*Cx is tiny and the state must
+// not be rounded to bf16 before its first use.
+//   out[b,ho,wo,co] = sum_{c,r,s} in[b,c,ho*st+r-pad,wo*st+s-pad] * w[co][c][r][s] (+ add[b,ho,wo,co]) (+ vec[b][co])
+// Encoder.conv1 (modules_DANRA_conditional.py:178-183, :260) is linear in its input channels, so the conditioning
+// channels' contribution is computed once per sampling job (out_f32) and added each step through `add`.
+// CTA: 8x8 output pixels x 64 channels, 256 threads (thread = pixel p, channel group cg of 16).
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ in, int Cx, int Hi, int Wi,
+                                                        const float* __restrict__ w,  // [64][Cx][KS][KS]
+                                                        int w_cstride_total,          // channels in the full weight (Cin_total)
+                                                        int w_coffset,                // first weight channel used
+                                                        const float* __restrict__ add,  // [B,Ho,Wo,64] fp32 or null
+                                                        const float* __restrict__ vec, int vec_stride,  // [B][..] or null
+                                                        bf16* __restrict__ out_bf16, float* __restrict__ out_f32, int Ho,
+                                                        int Wo, int pad) {
+    constexpr int PT = 8;                         // output tile side
+    constexpr int IT = (PT - 1) * STRIDE + KS;    // input tile side
+    __shared__ float s_in[IT][IT + 1];
+    __shared__ float s_w[KS * KS][64];
+    const int b = blockIdx.z;
+    const int ho0 = blockIdx.y * PT, wo0 = blockIdx.x * PT;
+    const int p = threadIdx.x & 63, cg = threadIdx.x >> 6;
+    const int py = p >> 3, px = p & 7;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int c = 0; c < Cx; ++c) {
+        __syncthreads();
+        const float* ip = in + ((size_t)b * Cx + c) * Hi * Wi;
+        for (int i = threadIdx.x; i < IT * IT; i += 256) {
+            const int iy = i / IT, ix = i - iy * IT;
+            const int gy = ho0 * STRIDE - pad + iy, gx = wo0 * STRIDE - pad + ix;
+            s_in[iy][ix] = (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) ? ip[(size_t)gy * Wi + gx] : 0.f;
+        }
+        for (int i = threadIdx.x; i < KS * KS * 64; i += 256) {
+            const int co = i & 63, tap = i >> 6;
+            s_w[tap][co] = w[((size_t)co * w_cstride_total + (w_coffset + c)) * (KS * KS) + tap];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int r = 0; r < KS; ++r) {
+#pragma unroll
+            for (int s = 0; s < KS; ++s) {
+                const float v = s_in[py * STRIDE + r][px * STRIDE + s];
+                const float4* wv = reinterpret_cast<const float4*>(&s_w[r * KS + s][cg * 16]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w4 = wv[q];
+                    acc[q * 4 + 0] = fmaf(v, w4.x, acc[q * 4 + 0]);
+                    acc[q * 4 + 1] = fmaf(v, w4.y, acc[q * 4 + 1]);
+                    acc[q * 4 + 2] = fmaf(v, w4.z, acc[q * 4 + 2]);
+                    acc[q * 4 + 3] = fmaf(v, w4.w, acc[q * 4 + 3]);
+                }
+            }
+        }
+    }
+    const int ho = ho0 + py, wo = wo0 + px;
+    if (ho >= Ho || wo >= Wo) return;
+    const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * 64 + cg * 16;
+    if (add) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] += add[o + i];
+    }
+    if (vec) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] += vec[(size_t)b * vec_stride + cg * 16 + i];
+    }
+    if (out_f32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) out_f32[o + i] = acc[i];
+    } else {
+        uint4 v0, v1;
+        v0.x = pack_bf16(acc[0], acc[1]);   v0.y = pack_bf16(acc[2], acc[3]);
+        v0.z = pack_bf16(acc[4], acc[5]);   v0.w = pack_bf16(acc[6], acc[7]);
+        v1.x = pack_bf16(acc[8], acc[9]);   v1.y = pack_bf16(acc[10], acc[11]);
+        v1.z = pack_bf16(acc[12], acc[13]); v1.w = pack_bf16(acc[14], acc[15]);
+        uint4* op = reinterpret_cast<uint4*>(out_bf16 + o);
+        op[0] = v0;
+        op[1] = v1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ InstanceNorm
+// Statistics of an NHWC bf16 tensor per (sample, channel) plane: stats[b][c] = {sum, sum of squares} (fp32 atomics,
+// buffer zeroed at the start of the step).  CTA = 32 channel-pair lanes x 8 pixel lanes over a slab of pixels.
+__global__ void __launch_bounds__(256) plane_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int HW,
+                                                          int C, int pix_per_cta) {
+    __shared__ float s_sum[8][64], s_sq[8][64];
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 64;
+    const int cl = (threadIdx.x & 31) * 2, pl = threadIdx.x >> 5;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int p1 = min(p0 + pix_per_cta, HW);
+    float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const bf16* xb = x + (size_t)b * HW * C + c0 + cl;
+    for (int p = p0 + pl; p < p1; p += 8) {
+        const float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(xb + (size_t)p * C));
+        a0 += v.x; a1 += v.y;
+        q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+    }
+    s_sum[pl][cl] = a0; s_sum[pl][cl + 1] = a1;
+    s_sq[pl][cl] = q0;  s_sq[pl][cl + 1] = q1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
+        float* st = stats + ((size_t)b * C + c0 + threadIdx.x) * 2;
+        atomicAdd(st, s);
+        atomicAdd(st + 1, q);
+    }
+}
+
+// y = (x - mean) * rstd (+ skip) (+ vec[b][c]); mean/rstd from stats (biased variance, eps 1e-5: InstanceNorm2d defaults,
+// modules_DANRA_conditional.py:409,417).  8 channels (16 B) per thread.
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                                                             const bf16* __restrict__ skip, const float* __restrict__ vec,
+                                                             int vec_stride, bf16* __restrict__ y, int HW, int C,
+                                                             size_t total_vec8) {
+    const float inv_hw = 1.0f / (float)HW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec8; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = i * 8;
+        const int c = (int)(e % C);
+        const int b = (int)(e / ((size_t)HW * C));
+        const uint4 xv = *reinterpret_cast<const uint4*>(x + e);
+        float f[8];
+        float2 t;
+        t = unpack_bf16(xv.x); f[0] = t.x; f[1] = t.y;
+        t = unpack_bf16(xv.y); f[2] = t.x; f[3] = t.y;
+        t = unpack_bf16(xv.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_bf16(xv.w); f[6] = t.x; f[7] = t.y;
+        const float* st = stats + ((size_t)b * C + c) * 2;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float mean = st[2 * j] * inv_hw;
+            const float var = fmaxf(st[2 * j + 1] * inv_hw - mean * mean, 0.f);
+            f[j] = (f[j] - mean) * rsqrtf(var + 1e-5f);
+        }
+        if (skip) {
+            const uint4 sv = *reinterpret_cast<const uint4*>(skip + e);
+            t = unpack_bf16(sv.x); f[0] += t.x; f[1] += t.y;
+            t = unpack_bf16(sv.y); f[2] += t.x; f[3] += t.y;
+            t = unpack_bf16(sv.z); f[4] += t.x; f[5] += t.y;
+            t = unpack_bf16(sv.w); f[6] += t.x; f[7] += t.y;
+        }
+        if (vec) {
+            const float* vp = vec + (size_t)b * vec_stride + c;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += vp[j];
+        }
+        uint4 o;
+        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(y + e) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tail convolution
+// Decoder.final_layer (modules_DANRA_conditional.py:503-509): InstanceNorm(ConvT out) -> Conv3x3(64 -> c_out) + bias, fp32 NCHW
+// result (eps_hat).  Cout is 1 (or a few): a 576-long reduction per pixel, not a GEMM.  The normalisation is applied on
+// the fly; zero padding applies to the *normalised* tensor, so out-of-image taps contribute nothing.
+// One warp per output pixel row segment: lane <-> channel pair; warp-reduce over 64 channels.
+__global__ void __launch_bounds__(256) tail_conv_kernel(const bf16* __restrict__ x,      // [B,H,W,64] (un-normalised)
+                                                        const float* __restrict__ stats,  // [B][64][2]
+                                                        const float* __restrict__ w,      // [c_out][64][3][3]
+                                                        const float* __restrict__ bias, float* __restrict__ out,  // [B,c_out,H,W]
+                                                        int H, int W, int c_out) {
+    __shared__ float s_w[9][64];
+    __shared__ float s_mean[64], s_rstd[64];
+    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 64) {
+        const float inv = 1.0f / (float)(H * W);
+        const float* st = stats + ((size_t)b * 64 + threadIdx.x) * 2;
+        const float mean = st[0] * inv;
+        const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
+        s_mean[threadIdx.x] = mean;
+        s_rstd[threadIdx.x] = rsqrtf(var + 1e-5f);
+    }
+    for (int oc = 0; oc < c_out; ++oc) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 9 * 64; i += 256) {
+            const int c = i & 63, tap = i >> 6;
+            s_w[tap][c] = w[((size_t)oc * 64 + c) * 9 + tap];
+        }
+        __syncthreads();
+        const int c = lane * 2;
+        const float m0 = s_mean[c], m1 = s_mean[c + 1], r0 = s_rstd[c], r1 = s_rstd[c + 1];
+        // CTA covers 8 rows x 32 cols of pixels; each warp one row, looping over the 32 columns
+        const int h = blockIdx.y * 8 + warp;
+        if (h < H) {
+            for (int wx = 0; wx < 32; ++wx) {
+                const int wcol = blockIdx.x * 32 + wx;
+                if (wcol >= W) break;
+                float acc = 0.f;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const int hi = h + r - 1;
+                    if (hi < 0 || hi >= H) continue;
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const int wi = wcol + s - 1;
+                        if (wi < 0 || wi >= W) continue;
+                        const float2 v = __bfloat1622float2(
+                            *reinterpret_cast<const bf162*>(x + (((size_t)b * H + hi) * W + wi) * 64 + c));
+                        acc = fmaf((v.x - m0) * r0, s_w[r * 3 + s][c], acc);
+                        acc = fmaf((v.y - m1) * r1, s_w[r * 3 + s][c + 1], acc);
+                    }
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) out[(((size_t)b * c_out + oc) * H + h) * W + wcol] = acc + bias[oc];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ posterior update
+// diffusion_DANRA_conditional.py:135-157:  x <- (1/sqrt(alpha_i)) * (x - ((1-alpha_i)/sqrt(1-alpha_hat_i)) * eps) + sqrt(beta_i) * z
+// with coefficients indexed by i itself, z = 0 at i == 1.  Same op order as the reference and no FMA contraction so that
+// identical eps/z give bit-identical x.  z is either host-provided (noise[i][...], parity runs) or drawn in-kernel from
+// Philox4x32-10 keyed by (seed; global sample index, element, step) so results do not depend on how the batch is sharded.
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    c[0] = hi1 ^ c[1] ^ k0;
+    c[1] = lo1;
+    c[2] = hi0 ^ c[3] ^ k1;
+    c[3] = lo0;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
+    const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;  // (0,1]
+    const float u2 = (float)b * 2.3283064365386963e-10f;
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+}
+
+// step_ptr[0] holds the current i (device-resident so one captured graph is replayed for every step).
+// t_arr[b] is rewritten to i-1 for the next evaluation.  4 elements per thread.
+__global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
+                                                               const float* __restrict__ noise,  // [T][n] or null
+                                                               const float* __restrict__ alphas, const float* __restrict__ betas,
+                                                               const float* __restrict__ alpha_hat, int* __restrict__ step_ptr,
+                                                               int* __restrict__ t_arr, int B, size_t n, size_t per_sample,
+                                                               unsigned long long seed, unsigned long long sample_offset,
+                                                               float noise_scale) {
+    const int i = *step_ptr;
+    const float alpha = alphas[i], beta = betas[i], ahat = alpha_hat[i];
+    const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(alpha));
+    const float c2 = __fdiv_rn(__fsub_rn(1.0f, alpha), __fsqrt_rn(__fsub_rn(1.0f, ahat)));
+    const float c3 = __fsqrt_rn(beta);
+    const size_t n4 = n >> 2;
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n4; v += (size_t)gridDim.x * blockDim.x) {
+        float4 xv = reinterpret_cast<float4*>(x)[v];
+        const float4 ev = reinterpret_cast<const float4*>(eps)[v];
+        float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i > 1) {
+            if (noise) {
+                zv = reinterpret_cast<const float4*>(noise + (size_t)i * n)[v];
+            } else {
+                const size_t e = v * 4;
+                const unsigned long long sample = sample_offset + e / per_sample;
+                const unsigned long long within = (e % per_sample) >> 2;
+                uint32_t c[4] = {(uint32_t)within, (uint32_t)i, (uint32_t)sample, (uint32_t)(sample >> 32)};
+                philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+                const float2 g0 = box_muller(c[0], c[1]), g1 = box_muller(c[2], c[3]);
+                zv = make_float4(g0.x * noise_scale, g0.y * noise_scale, g1.x * noise_scale, g1.y * noise_scale);
+            }
+        }
+        xv.x = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.x, __fmul_rn(c2, ev.x))), __fmul_rn(c3, zv.x));
+        xv.y = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.y, __fmul_rn(c2, ev.y))), __fmul_rn(c3, zv.y));
+        xv.z = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.z, __fmul_rn(c2, ev.z))), __fmul_rn(c3, zv.z));
+        xv.w = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.w, __fmul_rn(c2, ev.w))), __fmul_rn(c3, zv.w));
+        reinterpret_cast<float4*>(x)[v] = xv;
+    }
+}
+// Runs after the update (stream order): i <- i-1 and t[b] <- i-1 for the next UNet evaluation.
+__global__ void step_advance_kernel(int* step_ptr, int* t_arr, int B) {
+    const int i = *step_ptr - 1;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) t_arr[b] = i;
+    if (threadIdx.x == 0) *step_ptr = i;
+}
+
+__global__ void fill_int_kernel(int* p, int v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace b2d

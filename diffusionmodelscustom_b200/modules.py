@@ -1,0 +1,344 @@
+"""Drop-in model classes for the reference's sampling path (Family R), backed by the native B200 library.
+
+Mirrors the constructor signatures, attribute names and ``state_dict`` keys of
+``DDPM_DANRA_conditional/modules_DANRA_conditional.py`` (``Encoder`` :117-199, ``DecoderBlock`` :349-422,
+``Decoder`` :465-569, ``DiffusionNet`` :571-616) — and therefore of the byte-near duplicate
+``modules_DANRA_flexible.py``.  The ``nn.Module`` tree below only *holds parameters* (so that
+``load_state_dict`` / ``state_dict`` / ``.to()`` behave as in the reference); all arithmetic of
+``DiffusionNet.forward`` runs in ``libb200ddpm.so`` through the C ABI of ``include/b200ddpm.h``.
+There is no PyTorch/CPU execution path: calling ``forward`` without the CUDA library or a CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+FMAP_CHANNELS = [64, 64, 128, 256, 512]   # modules_DANRA_conditional.py:170
+
+
+class SinusoidalEmbedding(nn.Module):
+    """Parameter-free placeholder (modules_DANRA_conditional.py:17-63); evaluated inside temb_project_kernel."""
+
+    def __init__(self, dim_size, n: int = 10000):
+        assert dim_size % 2 == 0, 'dim_size must be even'
+        super().__init__()
+        self.dim_size = dim_size
+        self.n = n
+
+
+class ImageSelfAttention(nn.Module):
+    """Parameter holder for modules_DANRA_conditional.py:67-110 (keys ``layernorm.*``, ``attention.*``)."""
+
+    def __init__(self, input_channels: int, n_heads: int):
+        super().__init__()
+        self.input_channels = input_channels
+        self.n_heads = n_heads
+        self.layernorm = nn.LayerNorm(self.input_channels)
+        self.attention = nn.MultiheadAttention(self.input_channels, self.n_heads, batch_first=True)
+
+
+class _BasicBlock(nn.Module):
+    """Parameter holder with torchvision ``BasicBlock`` keys (conv1, bn1, conv2, bn2, downsample.{0,1})."""
+
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(cout)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+        for m in (self.conv1, self.conv2):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+
+def _time_projection(time_embedding, ch):
+    return nn.Sequential(nn.SiLU(), nn.Linear(time_embedding, ch))
+
+
+class Encoder(nn.Module):
+    """ResNet-18-shaped encoder of the reference (modules_DANRA_conditional.py:117-312); parameter holder."""
+
+    def __init__(self, input_channels: int, time_embedding: int, block=None, block_layers: list = [2, 2, 2, 2],
+                 n_heads: int = 4, num_classes: int = None, lsm_tensor=None, topo_tensor=None, cond_on_img=False,
+                 cond_img_dim=None):
+        super().__init__()
+        if list(block_layers) != [2, 2, 2, 2]:
+            raise NotImplementedError("only block_layers=[2,2,2,2] (BasicBlock) is built; the reference's Decoder "
+                                      "asserts against those widths too (modules_DANRA_conditional.py:442)")
+        if time_embedding != 256:
+            raise NotImplementedError("time_embedding must be 256 (every reference driver uses 256)")
+        self.block_layers = block_layers
+        self.time_embedding = time_embedding
+        self.hr_channels = input_channels
+        self.input_channels = input_channels
+        self.n_heads = n_heads
+        self.num_classes = num_classes
+        self.cond_channels = 0
+        if lsm_tensor is not None:
+            self.register_buffer('lsm', lsm_tensor)
+            self.input_channels += 1
+        if topo_tensor is not None:
+            self.register_buffer('elevation', topo_tensor)
+            self.input_channels += 1
+        if cond_on_img:
+            self.input_channels += cond_img_dim[0]
+            self.cond_channels = cond_img_dim[0]
+        self.sinusiodal_embedding = SinusoidalEmbedding(self.time_embedding)
+        self.bn1 = nn.BatchNorm2d(64)
+        cin = 64
+        for li, cout in enumerate(FMAP_CHANNELS[1:], start=1):
+            setattr(self, f"layer{li}", nn.Sequential(_BasicBlock(cin, cout, 1 if li == 1 else 2),
+                                                      _BasicBlock(cout, cout, 1)))
+            cin = cout
+        self.time_projection_layers = nn.ModuleList([_time_projection(time_embedding, ch) for ch in FMAP_CHANNELS])
+        self.attention_layers = nn.ModuleList([ImageSelfAttention(ch, n_heads) for ch in FMAP_CHANNELS])
+        self.conv1 = nn.Conv2d(self.input_channels, 64, kernel_size=(8, 8), stride=(2, 2), padding=(3, 3), bias=False)
+        self.conv2 = nn.Conv2d(64, 64, kernel_size=(8, 8), stride=(2, 2), padding=(3, 3), bias=False)
+        if num_classes is not None:
+            self.label_emb = nn.Embedding(num_classes, time_embedding)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("Encoder is evaluated only as part of DiffusionNet.forward (fused native program)")
+
+
+class DecoderBlock(nn.Module):
+    """Parameter holder for modules_DANRA_conditional.py:349-460."""
+
+    def __init__(self, input_channels: int, output_channels: int, time_embedding: int, upsample_scale: int = 2,
+                 activation: nn.Module = nn.ReLU, compute_attn: bool = True, n_heads: int = 4):
+        super().__init__()
+        if upsample_scale != 2:
+            raise NotImplementedError("upsample_scale must be 2")
+        self.input_channels = input_channels
+        self.output_channels = output_channels
+        self.upsample_scale = upsample_scale
+        self.time_embedding = time_embedding
+        self.compute_attn = compute_attn
+        self.n_heads = n_heads
+        self.attention = ImageSelfAttention(output_channels, n_heads) if compute_attn else nn.Identity()
+        self.sinusiodal_embedding = SinusoidalEmbedding(self.time_embedding)
+        self.time_projection_layer = _time_projection(time_embedding, output_channels)
+        self.transpose = nn.ConvTranspose2d(input_channels, input_channels, kernel_size=2, stride=2)
+        self.instance_norm1 = nn.InstanceNorm2d(input_channels)
+        self.conv = nn.Conv2d(input_channels, output_channels, kernel_size=3, stride=1, padding=1)
+        self.instance_norm2 = nn.InstanceNorm2d(output_channels)
+        self.activation = activation()
+
+
+class Decoder(nn.Module):
+    """Parameter holder for modules_DANRA_conditional.py:465-569."""
+
+    def __init__(self, last_fmap_channels: int, output_channels: int, time_embedding: int, first_fmap_channels: int = 64,
+                 n_heads: int = 4):
+        super().__init__()
+        if last_fmap_channels != 512 or first_fmap_channels != 64:
+            raise NotImplementedError("Decoder widths are fixed to 512 -> 64 by the encoder (SURVEY.md §0.3)")
+        self.last_fmap_channels = last_fmap_channels
+        self.output_channels = output_channels
+        self.time_embedding = time_embedding
+        self.first_fmap_channels = first_fmap_channels
+        self.n_heads = n_heads
+        self.residual_layers = self.make_layers()
+        self.final_layer = DecoderBlock(self.residual_layers[-1].input_channels, self.output_channels,
+                                        time_embedding=self.time_embedding, activation=nn.Identity, compute_attn=False,
+                                        n_heads=self.n_heads)
+        self.final_layer.instance_norm2 = nn.Identity()
+
+    def make_layers(self, n: int = 4):
+        layers = []
+        for i in range(n):
+            in_ch = self.last_fmap_channels if i == 0 else layers[i - 1].output_channels
+            out_ch = in_ch // 2 if i != (n - 1) else self.first_fmap_channels
+            layers.append(DecoderBlock(in_ch, out_ch, time_embedding=self.time_embedding, compute_attn=True,
+                                       n_heads=self.n_heads))
+        return nn.ModuleList(layers)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("Decoder is evaluated only as part of DiffusionNet.forward (fused native program)")
+
+
+class NativeModel(nn.Module):
+    """Owns the opaque ``b2d_handle`` of a model and keeps it in sync with the module's parameters."""
+
+    _family = N.FAMILY_R
+
+    def __init__(self):
+        super().__init__()
+        self._h = None
+        self._h_key = None
+        self._w_version = None
+        self._cond_key = None
+        self._sched_key = None
+        self._max_batch = 0
+        self.debug_simt_conv = False
+
+    # -- to be provided by subclasses
+    def _config(self, img_size: int, max_batch: int) -> N.Config:
+        raise NotImplementedError
+
+    def _weights_version(self):
+        return tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + \
+            tuple(t.data_ptr() for t in self.parameters())
+
+    def _release(self):
+        if self._h is not None:
+            N.lib().b2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure(self, batch: int, img_size: int, device):
+        if device.type != "cuda":
+            raise N.NativeError("DiffusionNet/UNet_downscale run only on CUDA (sm_100a); there is no CPU path. "
+                                "Move the inputs to a B200 device.")
+        ver = self._weights_version()
+        key = (img_size, device.index, bool(self.debug_simt_conv))
+        if self._h is not None and (self._h_key != key or self._w_version != ver or batch > self._max_batch):
+            self._release()
+        if self._h is None:
+            L = N.lib()
+            self._max_batch = max(batch, self._max_batch)
+            cfg = self._config(img_size, self._max_batch)
+            h = C.c_void_p()
+            with torch.cuda.device(device):
+                N.check(L.b2d_create(C.byref(cfg), C.byref(h)))
+                self._h = h
+                sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in self.state_dict().items()
+                      if v.dtype.is_floating_point}
+                arr = (N.Tensor * len(sd))()
+                for i, (k, v) in enumerate(sd.items()):
+                    arr[i].name = k.encode()
+                    arr[i].data = v.data_ptr()
+                    arr[i].ndim = v.dim()
+                    for d in range(v.dim()):
+                        arr[i].shape[d] = v.shape[d]
+                N.check(L.b2d_load_weights(self._h, arr, len(sd)))
+            self._h_key, self._w_version = key, ver
+            self._cond_key = None
+            self._sched_key = None
+        return self._h
+
+    @staticmethod
+    def _f32c(t, name):
+        if t is None:
+            return None
+        if not t.is_cuda:
+            raise N.NativeError(f"{name} must be a CUDA tensor (no CPU path)")
+        return t.detach().to(torch.float32).contiguous()
+
+    @staticmethod
+    def _tkey(t):
+        return None if t is None else (t.data_ptr(), int(t._version), tuple(t.shape))
+
+    def debug_read(self, name: str, batch: int):
+        """Bring-up aid: named intermediate activation of the last evaluation as NCHW fp32 (CPU)."""
+        buf = torch.empty(batch * 128 * 128 * 64, dtype=torch.float32)
+        c, hw = C.c_int32(), C.c_int32()
+        N.check(N.lib().b2d_debug_read(self._h, name.encode(), buf.data_ptr(), buf.numel(), C.byref(c), C.byref(hw)))
+        n = batch * hw.value * hw.value * c.value
+        return buf[:n].reshape(batch, hw.value, hw.value, c.value).permute(0, 3, 1, 2).contiguous()
+
+    def launch_count(self) -> int:
+        return 0 if self._h is None else int(N.lib().b2d_last_launch_count(self._h))
+
+
+class DiffusionNet(NativeModel):
+    """``DiffusionNet(encoder, decoder)`` of modules_DANRA_conditional.py:571-616, evaluated natively.
+
+    ``forward(x, t, y, cond_img, lsm_cond, topo_cond)`` keeps the positional contract the sampler relies on
+    (diffusion_DANRA_conditional.py:146)."""
+
+    def __init__(self, encoder: Encoder, decoder: Decoder, lsm_tensor=None, topo_tensor=None, cond_on_img=False,
+                 cond_img_dim=None):
+        super().__init__()
+        self.encoder = encoder
+        self.decoder = decoder
+
+    def _config(self, img_size, max_batch):
+        e, d = self.encoder, self.decoder
+        return N.Config(family=N.FAMILY_R, img_size=img_size, max_batch=max_batch, c_hr=e.hr_channels,
+                        c_out=d.output_channels, has_lsm=int(hasattr(e, "lsm")), has_topo=int(hasattr(e, "elevation")),
+                        cond_channels=e.cond_channels, num_classes=e.num_classes or 0, n_heads=e.n_heads, attn_ff=0,
+                        debug_simt_conv=int(self.debug_simt_conv))
+
+    def _set_conditioning(self, h, B, y, cond_img, lsm_cond, topo_cond, stream):
+        e = self.encoder
+        lsm = self._f32c(lsm_cond, "lsm_cond") if hasattr(e, "lsm") else None
+        topo = self._f32c(topo_cond, "topo_cond") if hasattr(e, "elevation") else None
+        cond = self._f32c(cond_img, "cond_img")
+        if hasattr(e, "lsm") and lsm is None:
+            raise ValueError("model was built with lsm_tensor: lsm_cond is required")
+        if hasattr(e, "elevation") and topo is None:
+            raise ValueError("model was built with topo_tensor: topo_cond is required")
+        yy = None
+        if y is not None:
+            if not y.is_cuda:
+                raise N.NativeError("y must be a CUDA tensor (no CPU path)")
+            yy = y.detach().to(torch.int64).contiguous()
+        key = (B, self._tkey(lsm_cond), self._tkey(topo_cond), self._tkey(cond_img), self._tkey(y))
+        if key != self._cond_key:
+            N.check(N.lib().b2d_set_conditioning(h, N.ptr(lsm), N.ptr(topo), N.ptr(cond), 0, 0, N.ptr(yy), B, stream))
+            self._cond_key = key
+            self._cond_refs = (lsm, topo, cond, yy)   # keep staging copies alive until consumed
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None,
+                cond_img: Optional[torch.Tensor] = None, lsm_cond: Optional[torch.Tensor] = None,
+                topo_cond: Optional[torch.Tensor] = None):
+        if x.dim() != 4 or x.shape[-1] != x.shape[-2]:
+            raise ValueError("x must be [B, C, H, H]")
+        B, _, H, _ = x.shape
+        h = self._ensure(B, H, x.device)
+        xx = self._f32c(x, "x")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._set_conditioning(h, B, y, cond_img, lsm_cond, topo_cond, stream)
+            out = torch.empty((B, self.decoder.output_channels, H, H), device=x.device, dtype=torch.float32)
+            th = t.detach().to("cpu", torch.int64).contiguous()
+            N.check(N.lib().b2d_forward(h, xx.data_ptr(), th.data_ptr(), out.data_ptr(), B, stream))
+        return out
+
+    @torch.no_grad()
+    def native_sample(self, x, y, cond_img, lsm_cond, topo_cond, betas, alphas, alpha_hat, noise=None, seed=0,
+                      sample_offset=0, noise_scale=1.0):
+        """Whole reverse loop on the device (CUDA graph); x is updated in place and returned."""
+        B, _, H, _ = x.shape
+        h = self._ensure(B, H, x.device)
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise N.NativeError("x must be a contiguous fp32 CUDA tensor")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            skey = (betas.data_ptr(), int(betas._version), len(betas))
+            if skey != self._sched_key:
+                b, a, ah = (v.detach().to("cpu", torch.float32).contiguous() for v in (betas, alphas, alpha_hat))
+                N.check(N.lib().b2d_set_schedule(h, b.data_ptr(), a.data_ptr(), ah.data_ptr(), len(b)))
+                self._sched_key = skey
+            self._set_conditioning(h, B, y, cond_img, lsm_cond, topo_cond, stream)
+            nz = self._f32c(noise, "noise")
+            N.check(N.lib().b2d_sample(h, x.data_ptr(), N.ptr(nz), int(seed), int(sample_offset), float(noise_scale), B,
+                                       stream))
+            if nz is not None:
+                torch.cuda.current_stream().synchronize()   # nz staging copy must outlive the queued work
+        return x
+
+
+# north_star alias: UNet(c_in, c_out, time_dim) style constructor over the same network
+def UNet(c_in: int = 1, c_out: int = 1, time_dim: int = 256, lsm: bool = False, topo: bool = False,
+         cond_channels: int = 0, num_classes=None, img_size: int = 64, n_heads: int = 4) -> DiffusionNet:
+    z = torch.zeros(1, img_size, img_size)
+    enc = Encoder(c_in, time_dim, n_heads=n_heads, num_classes=num_classes, lsm_tensor=z if lsm else None,
+                  topo_tensor=z.clone() if topo else None, cond_on_img=cond_channels > 0,
+                  cond_img_dim=(cond_channels, img_size, img_size) if cond_channels else None)
+    dec = Decoder(512, c_out, time_dim, 64, n_heads=n_heads)
+    return DiffusionNet(enc, dec)

@@ -1,0 +1,121 @@
+/*
+ * b200ddpm — C ABI of the B200-native DDPM reverse-diffusion sampling path.
+ *
+ * The reference (TheaQG/DiffusionModelsCustom) is pure Python and has no FFI; its "boundary" for this path is two
+ * duck-typed Python contracts:
+ *   sampler -> model : model(x, t, y, cond_img, lsm_cond, topo_cond)
+ *                      DDPM_DANRA_conditional/diffusion_DANRA_conditional.py:146, modules_DANRA_conditional.py:597-616
+ *                      (Family D: model(x, t, y_lowres), DDPM_clean_application/src/unet_ms.py:148)
+ *   script  -> sampler: DiffusionUtils(...).sample(x, model, y, cond_img, lsm_cond, topo_cond)
+ *                      DDPM_DANRA_conditional/diffusion_DANRA_conditional.py:105-159
+ * The entry points below are what a ctypes/cffi binding of those two calls needs; diffusionmodelscustom_b200/_native.py is
+ * that binding and INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative error code and never
+ * throws; b2d_last_error() returns the message of the calling thread's last failure.  Device pointers are caller-owned
+ * and must stay valid until the work queued on `stream` has completed.  A handle owns its packed weights, workspaces,
+ * TMA descriptors and CUDA graphs; it is bound to the CUDA device current at b2d_create() and is not thread-safe.
+ * `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ * There is no CPU fallback anywhere behind this ABI.
+ */
+#ifndef B200DDPM_H
+#define B200DDPM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_ABI_VERSION 1
+
+typedef struct b2d_handle b2d_handle;
+
+enum { B2D_FAMILY_R = 0, /* DiffusionNet(Encoder, Decoder): modules_DANRA_conditional.py / modules_DANRA_flexible.py */
+       B2D_FAMILY_D = 1  /* UNet_downscale: DDPM_clean_application/src/unet_ms.py */ };
+
+typedef struct b2d_config {
+    int32_t family;        /* B2D_FAMILY_R / B2D_FAMILY_D */
+    int32_t img_size;      /* H == W of the high-resolution field (power of two, 32..128) */
+    int32_t max_batch;     /* workspaces are sized for this many samples */
+    int32_t c_hr;          /* channels of x (Encoder(input_channels=...)), normally 1 */
+    int32_t c_out;         /* Decoder(output_channels=...), normally 1 */
+    int32_t has_lsm;       /* Encoder built with lsm_tensor (modules_DANRA_conditional.py:157-159) */
+    int32_t has_topo;      /* Encoder built with topo_tensor (:160-162) */
+    int32_t cond_channels; /* cond_img_dim[0] if cond_on_img else 0 (:163-164); Family D: channels of the low-res field */
+    int32_t num_classes;   /* label_emb rows, 0 = none (:194-196) */
+    int32_t n_heads;       /* attention heads (default 4) */
+    int32_t attn_ff;       /* 1: attention block has the LN-Linear-GELU-Linear tail (src/unet.py:91-96, unet_ms.py:13-18) */
+    int32_t debug_simt_conv; /* 1: run GEMM-shaped ops on the CUDA-core cross-check kernel (bring-up only) */
+} b2d_config;
+
+/* One named FP32 tensor of a reference state_dict (host memory, contiguous, torch layout). */
+typedef struct b2d_tensor {
+    const char* name;     /* reference key, e.g. "encoder.layer1.0.conv1.weight" */
+    const float* data;    /* host pointer, fp32 */
+    int32_t ndim;
+    int64_t shape[4];
+} b2d_tensor;
+
+const char* b2d_last_error(void);
+int b2d_abi_version(void);
+
+/* ---- handle life cycle ------------------------------------------------------------------------------------- */
+int b2d_create(const b2d_config* cfg, b2d_handle** out);
+void b2d_destroy(b2d_handle* h);
+
+/* Replaces `model.load_state_dict(torch.load(p)['network_params'])` (generation_DANRA_conditional.py:354-360):
+ * takes the reference's keys, folds eval-mode BatchNorm into the convolutions, re-packs to K-major bf16. */
+int b2d_load_weights(b2d_handle* h, const b2d_tensor* tensors, int32_t n);
+
+/* Schedule tables owned by DiffusionUtils (diffusion_DANRA_conditional.py:47-51): T floats each, host memory. */
+int b2d_set_schedule(b2d_handle* h, const float* betas, const float* alphas, const float* alpha_hat, int32_t T);
+
+/* Step-invariant conditioning of the current batch (device fp32, NCHW [B,1|C,H,W]; NULL = absent), y = int64 [B] season
+ * class (device) or NULL.  Family D: `cond` is the low-resolution field [B,C,h,w] with cond_h x cond_w pixels, which is
+ * bicubic-interpolated once (unet_ms.py:156).  Pre-computes everything that does not depend on x or t. */
+int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, const float* cond, int32_t cond_h,
+                         int32_t cond_w, const int64_t* y, int32_t B, void* stream);
+
+/* One eps_hat = model(x, t, ...) evaluation.  x, eps_out: device fp32 [B,c_hr,H,W]; t: HOST int64 [B]. */
+int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps_out, int32_t B, void* stream);
+
+/* Whole reverse loop i = T-1 .. 1 on device memory (DiffusionUtils.sample, diffusion_DANRA_conditional.py:127-157).
+ * x_inout: device fp32 [B,c_hr,H,W], x_T in / x_0 out.  noise: device fp32 [T][B*c_hr*H*W] host-generated z_i indexed by
+ * i (parity runs) or NULL for in-kernel Philox keyed by (seed, sample_offset + sample index, i).
+ * noise_scale multiplies z (1.0; 0.005 for data_scaled, src/diffusion_modules.py:173-174). */
+int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed, uint64_t sample_offset,
+               float noise_scale, int32_t B, void* stream);
+
+/* End-to-end entry with HOST buffers: uploads x_T and the conditioning, runs b2d_sample, downloads x_0, synchronises. */
+int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, const float* topo_host,
+                    const float* cond_host, int32_t cond_h, int32_t cond_w, const int64_t* y_host,
+                    const float* noise_host, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B);
+
+/* Kernel launches issued by the last b2d_forward / b2d_sample on this handle (graph nodes x replays). */
+int64_t b2d_last_launch_count(const b2d_handle* h);
+/* Bring-up aid: copies a named NHWC bf16 activation of the last evaluation ("fmap1".."fmap5", "dec0".."dec3", ...) to
+ * host fp32 [B,hw,hw,C]; synchronises the device. */
+int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out);
+
+/* ---- single operators (unit-test / profiling entry points; all pointers are device memory) ------------------ */
+/* NHWC bf16 convolution / projection through the same kernels the model uses.
+ * w_packed: bf16 [Cout][R*S*Cin] (convt: [(a*2+b)*CoutT+co][Cin]); impl 0 = tcgen05, 1 = CUDA-core cross-check. */
+int b2d_op_conv2d(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* residual_bf16,
+                  const float* post_add, int32_t post_stride, void* out_bf16, int32_t B, int32_t Hi, int32_t Wi,
+                  int32_t Cin, int32_t Cout, int32_t R, int32_t S, int32_t stride, int32_t pad, int32_t convt,
+                  int32_t act, int32_t impl, void* stream);
+int b2d_op_layernorm(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16, int32_t rows, int32_t C,
+                     void* stream);
+int b2d_op_attention(const void* qkv_bf16, void* o_bf16, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream);
+int b2d_op_instnorm(const void* x_bf16, const void* skip_bf16, const float* vec, int32_t vec_stride, void* y_bf16,
+                    float* stats_ws, int32_t B, int32_t HW, int32_t C, void* stream);
+int b2d_op_posterior_update(float* x, const float* eps, const float* z_or_null, const float* betas, const float* alphas,
+                            const float* alpha_hat, int32_t i, int32_t B, int64_t per_sample, uint64_t seed,
+                            uint64_t sample_offset, float noise_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DDPM_H */

@@ -1,0 +1,169 @@
+"""GPU unit tests of every kernel class through the C ABI, against plain torch FP32 on the CPU.
+
+Inputs are rounded to bf16 first so the only differences are accumulation order and the bf16 rounding of the output
+(<= 2^-9 relative per element): tolerance 6e-3 relative L2 for bf16-output kernels, exact for the posterior update."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from diffusionmodelscustom_b200 import _native as N
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+TOL = 6e-3
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+CONV_CASES = [
+    # name, B, H, Cin, Cout, R, stride, pad
+    ("3x3_s1_c64_32px", 2, 32, 64, 64, 3, 1, 1),
+    ("3x3_s1_c128_16px", 3, 16, 128, 128, 3, 1, 1),
+    ("3x3_s1_c512_2px_tn32", 5, 2, 512, 512, 3, 1, 1),
+    ("3x3_s1_c256_1px", 3, 1, 256, 256, 3, 1, 1),
+    ("3x3_s2_c64_to128", 2, 16, 64, 128, 3, 2, 1),
+    ("3x3_s2_c256_to512_4px", 4, 4, 256, 512, 3, 2, 1),
+    ("1x1_s2_downsample", 2, 16, 64, 128, 1, 2, 0),
+    ("8x8_s2_conv2", 2, 32, 64, 64, 8, 2, 3),
+    ("8x8_s2_conv2_64px", 1, 64, 64, 64, 8, 2, 3),
+    ("1x1_linear_qkv", 2, 16, 128, 384, 1, 1, 0),
+    ("3x3_s1_c64_64px_rowtile", 1, 64, 64, 64, 3, 1, 1),
+    ("3x3_s1_c64_128px", 1, 128, 64, 64, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_matches_torch(case, impl):
+    _, B, H, Cin, Cout, R, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case[0].encode()))
+    x = _bf(torch.randn(B, Cin, H, H, generator=g))
+    w = _bf(torch.randn(Cout, Cin, R, R, generator=g) / math.sqrt(Cin * R * R))
+    bias = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x, w, bias, stride, pad)
+    out = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, R, stride, pad, impl=impl)
+    assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_conv_full_epilogue(impl):
+    """bias -> +residual -> ReLU -> +per-sample channel vector (encoder stage tail) and GELU variant."""
+    B, H, C = 3, 8, 128
+    g = torch.Generator().manual_seed(5)
+    x = _bf(torch.randn(B, C, H, H, generator=g))
+    w = _bf(torch.randn(C, C, 3, 3, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(C, generator=g)
+    res = _bf(torch.randn(B, C, H, H, generator=g))
+    vec = torch.randn(B, 200, generator=g)   # stride 200, first C used
+    ref = F.relu(F.conv2d(x, w, bias, 1, 1) + res) + vec[:, :C, None, None]
+    out = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), G.nhwc_bf16(res), vec.cuda(), B, H, H, C, C, 3, 1, 1,
+                   act=1, impl=impl)
+    assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
+    ref2 = F.gelu(F.conv2d(x, w, bias, 1, 1))
+    out2 = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, C, C, 3, 1, 1, act=2, impl=impl)
+    assert G.rel_l2(G.to_nchw_f32(out2), ref2) < TOL
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("shape", [(2, 4, 512), (3, 16, 64), (1, 64, 64), (5, 2, 256)])
+def test_conv_transpose_matches_torch(shape, impl):
+    B, H, C = shape
+    g = torch.Generator().manual_seed(11)
+    x = _bf(torch.randn(B, C, H, H, generator=g))
+    w = _bf(torch.randn(C, C, 2, 2, generator=g) / math.sqrt(C))
+    bias = torch.randn(C, generator=g)
+    ref = F.conv_transpose2d(x, w, bias, stride=2)
+    out = G.conv2d(G.nhwc_bf16(x), G.pack_convt_weight(w), bias.cuda(), None, None, B, H, H, C, C, 1, 1, 0, convt=True, impl=impl)
+    assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 512])
+def test_layernorm(C):
+    g = torch.Generator().manual_seed(C)
+    rows = 333
+    x = _bf(torch.randn(rows, C, generator=g) * 3 + 1.5)
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    y = torch.empty(rows, C, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().b2d_op_layernorm(x.to(torch.bfloat16).cuda().data_ptr(), gamma.cuda().data_ptr(), beta.cuda().data_ptr(),
+                                     y.data_ptr(), rows, C, G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(y.float().cpu(), F.layer_norm(x, (C,), gamma, beta, 1e-5)) < TOL
+
+
+ATTN_CASES = [(2, 1024, 64, 4), (2, 256, 64, 4), (3, 64, 128, 4), (3, 16, 256, 4), (5, 4, 512, 4), (2, 1, 512, 4),
+              (2, 100, 64, 4), (2, 256, 64, 8), (1, 64, 128, 32), (2, 4096, 64, 4), (2, 16, 128, 1)]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}" for b, l, c, h in ATTN_CASES])
+def test_attention_matches_torch(case):
+    B, L, C, heads = case
+    d = C // heads
+    g = torch.Generator().manual_seed(L + C)
+    qkv = _bf(torch.randn(B, L, 3 * C, generator=g))
+    q, k, v = (t.reshape(B, L, heads, d).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(B, L, C)
+    o = torch.empty(B, L, C, dtype=torch.bfloat16, device="cuda")
+    N.check(N.lib().b2d_op_attention(qkv.to(torch.bfloat16).cuda().data_ptr(), o.data_ptr(), B, L, C, heads, G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(o.float().cpu(), ref) < 1e-2     # P is rounded to bf16 before P.V
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 512), (3, 1024, 64), (1, 16384, 64), (4, 4, 256)])
+def test_instance_norm_with_skip_and_vector(shape):
+    B, HW, C = shape
+    g = torch.Generator().manual_seed(HW)
+    x = _bf(torch.randn(B, HW, C, generator=g) * 2 + 0.7)
+    skip = _bf(torch.randn(B, HW, C, generator=g))
+    vec = torch.randn(B, C + 8, generator=g)
+    mean = x.mean(1, keepdim=True)
+    var = x.var(1, unbiased=False, keepdim=True)
+    ref = (x - mean) / torch.sqrt(var + 1e-5) + skip + vec[:, None, :C]
+    y = torch.empty(B, HW, C, dtype=torch.bfloat16, device="cuda")
+    ws = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
+    N.check(N.lib().b2d_op_instnorm(x.to(torch.bfloat16).cuda().data_ptr(), skip.to(torch.bfloat16).cuda().data_ptr(),
+                                    vec.cuda().data_ptr(), C + 8, y.data_ptr(), ws.data_ptr(), B, HW, C, G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(y.float().cpu(), ref) < TOL
+
+
+def test_posterior_update_bit_exact_with_host_noise():
+    """Same op order as diffusion_DANRA_conditional.py:155-157, no FMA contraction => identical bits."""
+    from oracle import ddpm_oracle as O
+    betas, alphas, ahat = O.schedule_tables(1000, 1e-4, 0.02)
+    g = torch.Generator().manual_seed(3)
+    for i in (999, 500, 2, 1):
+        x = torch.randn(3, 1, 64, 64, generator=g) * 50
+        eps = torch.randn(3, 1, 64, 64, generator=g)
+        z = torch.randn(3, 1, 64, 64, generator=g) if i > 1 else torch.zeros(3, 1, 64, 64)
+        ref = O.posterior_update(x, eps, z, i, betas, alphas, ahat)
+        xd = x.clone().cuda()
+        N.check(N.lib().b2d_op_posterior_update(xd.data_ptr(), eps.cuda().data_ptr(), z.cuda().data_ptr(),
+                                                betas.cuda().data_ptr(), alphas.cuda().data_ptr(), ahat.cuda().data_ptr(),
+                                                i, 3, 64 * 64, 0, 0, 1.0, G.stream()))
+        assert torch.equal(xd.cpu(), ref), i
+
+
+def test_posterior_update_philox_noise_is_standard_normal_and_shard_invariant():
+    from oracle import ddpm_oracle as O
+    betas, alphas, ahat = O.schedule_tables(1000, 1e-4, 0.02)
+    dev = [t.cuda() for t in (betas, alphas, ahat)]
+    B, per = 8, 64 * 64
+    zero = torch.zeros(B, 1, 64, 64, device="cuda")
+
+    def draw(batch, offset, i=700):
+        x = torch.zeros(batch, 1, 64, 64, device="cuda")
+        N.check(N.lib().b2d_op_posterior_update(x.data_ptr(), zero.data_ptr(), None, dev[0].data_ptr(), dev[1].data_ptr(),
+                                                dev[2].data_ptr(), i, batch, per, 1234, offset, 1.0, G.stream()))
+        return (x / torch.sqrt(betas[i]).item()).cpu()     # x = sqrt(beta) * z
+
+    z = draw(B, 0)
+    assert abs(float(z.mean())) < 0.02 and abs(float(z.std()) - 1.0) < 0.02
+    assert abs(float((z ** 4).mean()) - 3.0) < 0.15
+    # sample k of a shard starting at offset o draws the same z as global sample o+k
+    z_shard = draw(4, 4)
+    assert torch.equal(z_shard, z[4:])
+    assert not torch.equal(draw(B, 0, i=699), z)
