@@ -553,7 +553,17 @@ static int ensure_program(Handle* h, int B) {
 
 static int run_step_ops(Handle* h, cudaStream_t st) {
     if (h->stats_floats) B2D_CUDA(cudaMemsetAsync(h->d_stats, 0, h->stats_floats * sizeof(float), st));
-    for (auto& op : h->step_ops) B2D_TRY(op(st));
+    static const bool dbg = getenv("B2D_DEBUG_SYNC") != nullptr;
+    int idx = 0;
+    for (auto& op : h->step_ops) {
+        B2D_TRY(op(st));
+        if (dbg) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess)
+                return fail(-2, "step op #" + std::to_string(idx) + " failed: " + cudaGetErrorString(e));
+        }
+        ++idx;
+    }
     return 0;
 }
 

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     constexpr int PT = 8;                         // output tile side
     constexpr int IT = (PT - 1) * STRIDE + KS;    // input tile side
     __shared__ float s_in[IT][IT + 1];
-    __shared__ float s_w[KS * KS][64];
+    __shared__ __align__(16) float s_w[KS * KS][64];
     const int b = blockIdx.z;
     const int ho0 = blockIdx.y * PT, wo0 = blockIdx.x * PT;
     const int p = threadIdx.x & 63, cg = threadIdx.x >> 6;

@@ -88,8 +88,8 @@ def test_layernorm(C):
     x = _bf(torch.randn(rows, C, generator=g) * 3 + 1.5)
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
     y = torch.empty(rows, C, dtype=torch.bfloat16, device="cuda")
-    N.check(N.lib().b2d_op_layernorm(x.to(torch.bfloat16).cuda().data_ptr(), gamma.cuda().data_ptr(), beta.cuda().data_ptr(),
-                                     y.data_ptr(), rows, C, G.stream()))
+    xd, gd, bd = x.to(torch.bfloat16).cuda(), gamma.cuda(), beta.cuda()   # keep device copies alive across the call
+    N.check(N.lib().b2d_op_layernorm(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, C, G.stream()))
     torch.cuda.synchronize()
     assert G.rel_l2(y.float().cpu(), F.layer_norm(x, (C,), gamma, beta, 1e-5)) < TOL
 
@@ -107,7 +107,8 @@ def test_attention_matches_torch(case):
     q, k, v = (t.reshape(B, L, heads, d).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1))
     ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(B, L, C)
     o = torch.empty(B, L, C, dtype=torch.bfloat16, device="cuda")
-    N.check(N.lib().b2d_op_attention(qkv.to(torch.bfloat16).cuda().data_ptr(), o.data_ptr(), B, L, C, heads, G.stream()))
+    qd = qkv.to(torch.bfloat16).cuda()
+    N.check(N.lib().b2d_op_attention(qd.data_ptr(), o.data_ptr(), B, L, C, heads, G.stream()))
     torch.cuda.synchronize()
     assert G.rel_l2(o.float().cpu(), ref) < 1e-2     # P is rounded to bf16 before P.V
 
@@ -124,8 +125,9 @@ def test_instance_norm_with_skip_and_vector(shape):
     ref = (x - mean) / torch.sqrt(var + 1e-5) + skip + vec[:, None, :C]
     y = torch.empty(B, HW, C, dtype=torch.bfloat16, device="cuda")
     ws = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
-    N.check(N.lib().b2d_op_instnorm(x.to(torch.bfloat16).cuda().data_ptr(), skip.to(torch.bfloat16).cuda().data_ptr(),
-                                    vec.cuda().data_ptr(), C + 8, y.data_ptr(), ws.data_ptr(), B, HW, C, G.stream()))
+    xd, sd, vd = x.to(torch.bfloat16).cuda(), skip.to(torch.bfloat16).cuda(), vec.cuda()
+    N.check(N.lib().b2d_op_instnorm(xd.data_ptr(), sd.data_ptr(), vd.data_ptr(), C + 8, y.data_ptr(), ws.data_ptr(), B, HW, C,
+                                    G.stream()))
     torch.cuda.synchronize()
     assert G.rel_l2(y.float().cpu(), ref) < TOL
 
@@ -135,15 +137,15 @@ def test_posterior_update_bit_exact_with_host_noise():
     from oracle import ddpm_oracle as O
     betas, alphas, ahat = O.schedule_tables(1000, 1e-4, 0.02)
     g = torch.Generator().manual_seed(3)
+    bd, ad, hd = betas.cuda(), alphas.cuda(), ahat.cuda()
     for i in (999, 500, 2, 1):
         x = torch.randn(3, 1, 64, 64, generator=g) * 50
         eps = torch.randn(3, 1, 64, 64, generator=g)
         z = torch.randn(3, 1, 64, 64, generator=g) if i > 1 else torch.zeros(3, 1, 64, 64)
         ref = O.posterior_update(x, eps, z, i, betas, alphas, ahat)
-        xd = x.clone().cuda()
-        N.check(N.lib().b2d_op_posterior_update(xd.data_ptr(), eps.cuda().data_ptr(), z.cuda().data_ptr(),
-                                                betas.cuda().data_ptr(), alphas.cuda().data_ptr(), ahat.cuda().data_ptr(),
-                                                i, 3, 64 * 64, 0, 0, 1.0, G.stream()))
+        xd, ed, zd = x.clone().cuda(), eps.cuda(), z.cuda()
+        N.check(N.lib().b2d_op_posterior_update(xd.data_ptr(), ed.data_ptr(), zd.data_ptr(), bd.data_ptr(), ad.data_ptr(),
+                                                hd.data_ptr(), i, 3, 64 * 64, 0, 0, 1.0, G.stream()))
         assert torch.equal(xd.cpu(), ref), i
 
 
