@@ -15,7 +15,7 @@ FAMILY_R, FAMILY_D = 0, 1
 
 # every symbol include/b200ddpm.h declares (tests check that the library exports all of them)
 SYMBOLS = ["b2d_last_error", "b2d_abi_version", "b2d_create", "b2d_destroy", "b2d_load_weights", "b2d_set_schedule",
-           "b2d_set_conditioning", "b2d_forward", "b2d_sample", "b2d_sample_host", "b2d_last_launch_count", "b2d_debug_read",
+           "b2d_set_conditioning", "b2d_forward", "b2d_sample", "b2d_sample_host", "b2d_last_launch_count", "b2d_debug_read", "b2d_profile_step",
            "b2d_op_conv2d", "b2d_op_layernorm", "b2d_op_attention", "b2d_op_instnorm", "b2d_op_posterior_update"]
 
 
@@ -26,6 +26,11 @@ class Config(C.Structure):
 
 class Tensor(C.Structure):
     _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+class OpProfile(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("klass", C.c_char * 24), ("flops", C.c_double), ("bytes", C.c_double),
+                ("ms", C.c_double)]
 
 
 class NativeError(RuntimeError):
@@ -59,6 +64,8 @@ def lib():
         L.b2d_last_launch_count.argtypes = [C.c_void_p]
         L.b2d_last_launch_count.restype = C.c_int64
         L.b2d_debug_read.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        L.b2d_profile_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(OpProfile),
+                                       C.c_int32, C.POINTER(C.c_int32)]
         L.b2d_op_conv2d.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_void_p] + [C.c_int32] * 12 + [C.c_void_p]
         L.b2d_op_layernorm.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p]
         L.b2d_op_attention.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p]

@@ -4,7 +4,7 @@
 //   layernorm_rows_kernel : LayerNorm over C per token, fp32 statistics, one warp per token.
 //   flash_attn_kernel     : softmax(q k^T / sqrt(d)) v per (sample, head) with streaming (online) softmax —
 //                           the L x L score matrix the reference materialises (need_weights=True) never exists.
-//                           mma.sync m16n8k16 bf16 (these layers are ex2-bound at head_dim 16),
+//                           mma.sync m16n8k16 f16 (these layers are ex2-bound at head_dim 16),
 //                           K/V tiles double-buffered in shared memory with cp.async.
 // The QKV and output projections run through the tcgen05 GEMM path (conv.cuh, 1x1 case) with the residual add
 // (+ ReLU in the decoder) in its epilogue.
@@ -14,20 +14,20 @@
 namespace b2d {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-// x,y: [rows][C] bf16.  C in {64,...,512}, C % 64 == 0.  One warp per row, each lane owns C/32 contiguous pairs.
+// x,y: [rows][C] f16.  C in {64,...,512}, C % 64 == 0.  One warp per row, each lane owns C/32 contiguous pairs.
 template <int C>
-__global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, bf16* __restrict__ y,
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const f16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, f16* __restrict__ y,
                                                              int rows) {
     constexpr int PER = C / 32;  // elements per lane (2..16), contiguous
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= rows) return;
-    const bf16* xr = x + (size_t)warp * C + lane * PER;
+    const f16* xr = x + (size_t)warp * C + lane * PER;
     float v[PER];
 #pragma unroll
     for (int i = 0; i < PER; i += 2) {
-        const float2 t = __bfloat1622float2(*reinterpret_cast<const bf162*>(xr + i));
+        const float2 t = __half22float2(*reinterpret_cast<const f162*>(xr + i));
         v[i] = t.x;
         v[i + 1] = t.y;
     }
@@ -42,17 +42,17 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const bf16* __restr
         ss += d * d;
     }
     const float rstd = rsqrtf(warp_sum(ss) * (1.0f / C) + 1e-5f);
-    bf16* yr = y + (size_t)warp * C + lane * PER;
+    f16* yr = y + (size_t)warp * C + lane * PER;
 #pragma unroll
     for (int i = 0; i < PER; i += 2) {
         const int c = lane * PER + i;
         const float a = (v[i] - mean) * rstd * gamma[c] + beta[c];
         const float b = (v[i + 1] - mean) * rstd * gamma[c + 1] + beta[c + 1];
-        *reinterpret_cast<bf162*>(yr + i) = __floats2bfloat162_rn(a, b);
+        *reinterpret_cast<f162*>(yr + i) = __floats2half2_rn(a, b);
     }
 }
 
-inline int layernorm_launch(const bf16* x, const float* g, const float* b, bf16* y, int rows, int C, cudaStream_t st) {
+inline int layernorm_launch(const f16* x, const float* g, const float* b, f16* y, int rows, int C, cudaStream_t st) {
     const int blocks = (rows + 7) / 8;
     switch (C) {
         case 64: layernorm_rows_kernel<64><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
@@ -66,7 +66,7 @@ inline int layernorm_launch(const bf16* x, const float* g, const float* b, bf16*
 }
 
 // ------------------------------------------------------------------------------------------------ flash attention
-// qkv: [B*L][3C] bf16 (q | k | v, head j owns columns [j*D,(j+1)*D) of each third); o: [B*L][C] bf16.
+// qkv: [B*L][3C] f16 (q | k | v, head j owns columns [j*D,(j+1)*D) of each third); o: [B*L][C] f16.
 // grid = (ceil(L/64), heads, B); 128 threads; each warp owns 16 query rows; KV tiles of 64 keys.
 constexpr int FA_BQ = 64;
 constexpr int FA_BK = 64;
@@ -77,26 +77,26 @@ __host__ __device__ constexpr int fa_smem_bytes() {
 }
 
 template <int D>
-__global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int C,
+__global__ void __launch_bounds__(128) flash_attn_kernel(const f16* __restrict__ qkv, f16* __restrict__ o, int L, int C,
                                                          float scale_log2e) {
     constexpr int LDS = D + 8;  // padded row (elements): conflict-free 32-bit fragment loads and ldmatrix
     extern __shared__ __align__(16) uint8_t fa_smem[];
-    bf16* sK = reinterpret_cast<bf16*>(fa_smem);          // [2][FA_BK][LDS]
-    bf16* sV = sK + 2 * FA_BK * LDS;                      // [2][FA_BK][LDS]
+    f16* sK = reinterpret_cast<f16*>(fa_smem);          // [2][FA_BK][LDS]
+    f16* sV = sK + 2 * FA_BK * LDS;                      // [2][FA_BK][LDS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const int head = blockIdx.y, b = blockIdx.z;
     const int q0 = blockIdx.x * FA_BQ + warp * 16;
     const size_t row_stride = (size_t)3 * C;
-    const bf16* base = qkv + (size_t)b * L * row_stride + (size_t)head * D;
+    const f16* base = qkv + (size_t)b * L * row_stride + (size_t)head * D;
 
     // ---- Q fragments (A operand, 16 x D), rows q0+g and q0+g+8
     uint32_t qf[D / 16][4];
     {
         const int r0 = q0 + g, r1 = q0 + g + 8;
-        const bf16* p0 = base + (size_t)r0 * row_stride;
-        const bf16* p1 = base + (size_t)r1 * row_stride;
+        const f16* p0 = base + (size_t)r0 * row_stride;
+        const f16* p1 = base + (size_t)r1 * row_stride;
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
             const int c = kk * 16 + 2 * t;
@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict_
 
     auto load_tile = [&](int tile, int buf) {
         const int k0 = tile * FA_BK;
-        bf16* dK = sK + buf * FA_BK * LDS;
-        bf16* dV = sV + buf * FA_BK * LDS;
+        f16* dK = sK + buf * FA_BK * LDS;
+        f16* dV = sV + buf * FA_BK * LDS;
         for (int i = threadIdx.x; i < FA_BK * CPR; i += 128) {
             const int r = i / CPR, c = (i - r * CPR) * 8;
             const bool ok = (k0 + r) < L;
-            const bf16* src = base + (size_t)(ok ? (k0 + r) : 0) * row_stride + c;
+            const f16* src = base + (size_t)(ok ? (k0 + r) : 0) * row_stride + c;
             cp_async16(dK + r * LDS + c, src + C, ok);
             cp_async16(dV + r * LDS + c, src + 2 * C, ok);
         }
@@ -137,20 +137,20 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict_
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const bf16* tK = sK + buf * FA_BK * LDS;
-        const bf16* tV = sV + buf * FA_BK * LDS;
+        const f16* tK = sK + buf * FA_BK * LDS;
+        const f16* tV = sV + buf * FA_BK * LDS;
 
         // ---- S = Q K^T (16 x 64 per warp), fp32
         float s[FA_BK / 8][4];
 #pragma unroll
         for (int j = 0; j < FA_BK / 8; ++j) {
             s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-            const bf16* kr = tK + (j * 8 + g) * LDS + 2 * t;
+            const f16* kr = tK + (j * 8 + g) * LDS + 2 * t;
 #pragma unroll
             for (int kk = 0; kk < D / 16; ++kk) {
                 const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + kk * 16);
                 const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8);
-                mma_bf16_16816(s[j], qf[kk], b0, b1);
+                mma_f16_16816(s[j], qf[kk], b0, b1);
             }
         }
         // ---- mask keys beyond L (last tile only)
@@ -189,8 +189,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict_
             const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -ms1));
             rs0 += p0 + p1;
             rs1 += p2 + p3;
-            pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
-            pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+            pf[j >> 1][(j & 1) * 2 + 0] = pack_h2(p0, p1);
+            pf[j >> 1][(j & 1) * 2 + 1] = pack_h2(p2, p3);
         }
         l0 = l0 * corr0 + rs0;
         l1 = l1 * corr1 + rs1;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict_
             for (int i = 0; i < D / 8; ++i) {
                 uint32_t b0, b1;
                 ldmatrix_x2_trans(b0, b1, vrow + i * 16);
-                mma_bf16_16816(oacc[i], pf[kk], b0, b1);
+                mma_f16_16816(oacc[i], pf[kk], b0, b1);
             }
         }
         __syncthreads();  // everyone done with this buffer before it is refilled
@@ -223,31 +223,31 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const bf16* __restrict_
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     const int r0 = q0 + g, r1 = q0 + g + 8;
-    bf16* ob = o + (size_t)b * L * C + (size_t)head * D + 2 * t;
+    f16* ob = o + (size_t)b * L * C + (size_t)head * D + 2 * t;
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
         if (r0 < L)
-            *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * C + i * 8) = pack_bf16(oacc[i][0] * inv0, oacc[i][1] * inv0);
+            *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * C + i * 8) = pack_h2(oacc[i][0] * inv0, oacc[i][1] * inv0);
         if (r1 < L)
-            *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * C + i * 8) = pack_bf16(oacc[i][2] * inv1, oacc[i][3] * inv1);
+            *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * C + i * 8) = pack_h2(oacc[i][2] * inv1, oacc[i][3] * inv1);
     }
 }
 
 // Head dims below the m16n8k16 K extent (n_heads = 8 or H/2 in some reference scripts, e.g. test/unet_test.py:20-159):
 // one thread per query, K/V tiles of 128 keys in shared memory, online softmax in blocks of 8 keys.
 template <int D>
-__global__ void __launch_bounds__(128) attn_small_d_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, int L, int C,
+__global__ void __launch_bounds__(128) attn_small_d_kernel(const f16* __restrict__ qkv, f16* __restrict__ o, int L, int C,
                                                            float scale_log2e) {
     __shared__ float sK[128][D];
     __shared__ float sV[128][D];
     const int head = blockIdx.y, b = blockIdx.z;
     const int qi = blockIdx.x * 128 + threadIdx.x;
     const size_t rs = (size_t)3 * C;
-    const bf16* base = qkv + (size_t)b * L * rs + (size_t)head * D;
+    const f16* base = qkv + (size_t)b * L * rs + (size_t)head * D;
     float q[D], acc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        q[d] = qi < L ? __bfloat162float(base[(size_t)qi * rs + d]) * scale_log2e : 0.f;
+        q[d] = qi < L ? __half2float(base[(size_t)qi * rs + d]) * scale_log2e : 0.f;
         acc[d] = 0.f;
     }
     float m = -INFINITY, l = 0.f;
@@ -257,8 +257,8 @@ __global__ void __launch_bounds__(128) attn_small_d_kernel(const bf16* __restric
             const int kr = k0 + threadIdx.x;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                sK[threadIdx.x][d] = kr < L ? __bfloat162float(base[(size_t)kr * rs + C + d]) : 0.f;
-                sV[threadIdx.x][d] = kr < L ? __bfloat162float(base[(size_t)kr * rs + 2 * C + d]) : 0.f;
+                sK[threadIdx.x][d] = kr < L ? __half2float(base[(size_t)kr * rs + C + d]) : 0.f;
+                sV[threadIdx.x][d] = kr < L ? __half2float(base[(size_t)kr * rs + 2 * C + d]) : 0.f;
             }
         }
         __syncthreads();
@@ -290,9 +290,9 @@ __global__ void __launch_bounds__(128) attn_small_d_kernel(const bf16* __restric
     }
     if (qi < L) {
         const float inv = 1.0f / l;
-        bf16* op = o + ((size_t)b * L + qi) * C + (size_t)head * D;
+        f16* op = o + ((size_t)b * L + qi) * C + (size_t)head * D;
 #pragma unroll
-        for (int d = 0; d < D; ++d) op[d] = __float2bfloat16(acc[d] * inv);
+        for (int d = 0; d < D; ++d) op[d] = __float2half_rn(sat_h(acc[d] * inv));
     }
 }
 
@@ -304,7 +304,7 @@ inline int flash_attn_init_attrs() {
     return 0;
 }
 
-inline int flash_attn_launch(const bf16* qkv, bf16* o, int B, int L, int C, int heads, cudaStream_t st) {
+inline int flash_attn_launch(const f16* qkv, f16* o, int B, int L, int C, int heads, cudaStream_t st) {
     B2D_CHECK(C % heads == 0, "attention: C must be divisible by n_heads");
     const int D = C / heads;
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);

@@ -25,15 +25,36 @@ struct HostTensor {
     size_t numel() const { return v.size(); }
 };
 
-static inline uint16_t f2bf(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
+static inline uint16_t f2h(float f) {   // host fp32 -> fp16 bits (round to nearest even, saturating)
+    const float c = f > 65504.0f ? 65504.0f : (f < -65504.0f ? -65504.0f : f);
+    const __half h = __float2half_rn(c);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
 }
 
-typedef std::function<int(cudaStream_t)> Op;
+typedef std::function<int(cudaStream_t)> OpFn;
+// One kernel launch of the per-step program, with the algorithmic work it represents (for roofline reporting).
+struct Op {
+    std::string name;   // layer, e.g. "l2b0.c1"
+    std::string klass;  // kernel class, e.g. "conv_tc", "flash_attn"
+    double flops = 0;   // algorithmic FLOPs of this launch (2*M*N*K; attention 4*L^2*C per sample)
+    double bytes = 0;   // algorithmic HBM bytes of this launch (activations read + written, weights once)
+    OpFn fn;
+    int operator()(cudaStream_t st) const { return fn(st); }
+};
+struct OpList {
+    std::vector<Op> v;
+    Op pending;
+    void meta(const std::string& name, const std::string& klass, double flops, double bytes) {
+        pending.name = name; pending.klass = klass; pending.flops = flops; pending.bytes = bytes;
+    }
+    void push_back(OpFn f) {
+        pending.fn = std::move(f);
+        v.push_back(pending);
+        pending = Op();
+    }
+};
 
 struct Handle {
     b2d_config cfg{};
@@ -81,8 +102,8 @@ struct Handle {
     int graph_nodes = 0;
     int64_t last_launches = 0;
     cudaStream_t own_stream = nullptr;
-    struct Tap { const bf16* p; int C, hw; };
-    std::map<std::string, Tap> taps;  // named activations (NHWC bf16) readable through b2d_debug_read
+    struct Tap { const f16* p; int C, hw; };
+    std::map<std::string, Tap> taps;  // named activations (NHWC f16) readable through b2d_debug_read
 
     template <typename T>
     int alloc(T** p, size_t count) {
@@ -124,15 +145,15 @@ static int upload_f32(Handle* h, const std::string& role, const std::vector<floa
     h->dev[role] = d;
     return 0;
 }
-static int upload_bf16(Handle* h, const std::string& role, const std::vector<uint16_t>& v) {
-    bf16* d;
+static int upload_f16(Handle* h, const std::string& role, const std::vector<uint16_t>& v) {
+    f16* d;
     B2D_TRY(h->alloc(&d, v.size()));
     B2D_CUDA(cudaMemcpy(d, v.data(), v.size() * 2, cudaMemcpyHostToDevice));
     h->dev[role] = d;
     return 0;
 }
 
-// Conv2d weight [Cout][Cin][R][S] (+ optional eval-BatchNorm folding) -> bf16 [Cout][(r*S+s)*Cin+ci], fp32 bias.
+// Conv2d weight [Cout][Cin][R][S] (+ optional eval-BatchNorm folding) -> f16 [Cout][(r*S+s)*Cin+ci], fp32 bias.
 // BN fold: s = gamma/sqrt(running_var+1e-5); W' = W*s[co]; b' = beta - running_mean*s (+ conv bias*s).
 static int pack_conv(Handle* h, const std::string& role, const std::string& wkey, const std::string& bias_key,
                      const std::string& bn_prefix) {
@@ -161,12 +182,12 @@ static int pack_conv(Handle* h, const std::string& role, const std::string& wkey
             for (int r = 0; r < R; ++r)
                 for (int s = 0; s < S; ++s)
                     p[((size_t)co * R * S + (r * S + s)) * Cin + ci] =
-                        f2bf(w->v[(((size_t)co * Cin + ci) * R + r) * S + s] * scale[co]);
-    B2D_TRY(upload_bf16(h, role + ".w", p));
+                        f2h(w->v[(((size_t)co * Cin + ci) * R + r) * S + s] * scale[co]);
+    B2D_TRY(upload_f16(h, role + ".w", p));
     B2D_TRY(upload_f32(h, role + ".b", bias));
     return 0;
 }
-// ConvTranspose2d weight [Cin][Cout][2][2] -> bf16 [(a*2+b)*Cout+co][ci]; bias [Cout].
+// ConvTranspose2d weight [Cin][Cout][2][2] -> f16 [(a*2+b)*Cout+co][ci]; bias [Cout].
 static int pack_convt(Handle* h, const std::string& role, const std::string& prefix) {
     NEED(w, prefix + ".weight");
     NEED(b, prefix + ".bias");
@@ -177,8 +198,8 @@ static int pack_convt(Handle* h, const std::string& role, const std::string& pre
         for (int co = 0; co < Cout; ++co)
             for (int a = 0; a < 2; ++a)
                 for (int bb = 0; bb < 2; ++bb)
-                    p[((size_t)(a * 2 + bb) * Cout + co) * Cin + ci] = f2bf(w->v[(((size_t)ci * Cout + co) * 2 + a) * 2 + bb]);
-    B2D_TRY(upload_bf16(h, role + ".w", p));
+                    p[((size_t)(a * 2 + bb) * Cout + co) * Cin + ci] = f2h(w->v[(((size_t)ci * Cout + co) * 2 + a) * 2 + bb]);
+    B2D_TRY(upload_f16(h, role + ".w", p));
     B2D_TRY(upload_f32(h, role + ".b", b->v));
     return 0;
 }
@@ -186,8 +207,8 @@ static int pack_linear(Handle* h, const std::string& role, const std::string& wk
     NEED(w, wkey);
     NEED(b, bkey);
     std::vector<uint16_t> p(w->numel());
-    for (size_t i = 0; i < p.size(); ++i) p[i] = f2bf(w->v[i]);
-    B2D_TRY(upload_bf16(h, role + ".w", p));
+    for (size_t i = 0; i < p.size(); ++i) p[i] = f2h(w->v[i]);
+    B2D_TRY(upload_f16(h, role + ".w", p));
     B2D_TRY(upload_f32(h, role + ".b", b->v));
     return 0;
 }
@@ -287,11 +308,11 @@ struct Builder {
     Handle* h;
     int B;
     int err = 0;
-    std::vector<Op>& ops;
-    Builder(Handle* hh, int b, std::vector<Op>& o) : h(hh), B(b), ops(o) {}
+    OpList& ops;
+    Builder(Handle* hh, int b, OpList& o) : h(hh), B(b), ops(o) {}
 
-    bf16* act(size_t elems) {
-        bf16* p = nullptr;
+    f16* act(size_t elems) {
+        f16* p = nullptr;
         if (h->alloc(&p, elems) != 0) err = -2;
         return p;
     }
@@ -306,8 +327,8 @@ struct Builder {
     }
 
     // GEMM-shaped op through the tcgen05 kernel (or the SIMT cross-check when cfg.debug_simt_conv)
-    void conv(const bf16* in, int Hi, int Wi, int Cin, bf16* out, int Cout, int R, int stride, int pad, bool convt,
-              const std::string& role, const bf16* residual, const float* post_add, int post_stride, int act) {
+    void conv(const f16* in, int Hi, int Wi, int Cin, f16* out, int Cout, int R, int stride, int pad, bool convt,
+              const std::string& role, const f16* residual, const float* post_add, int post_stride, int act) {
         auto pl = std::make_shared<ConvPlan>();
         ConvParams& p = pl->p;
         memset(&p, 0, sizeof(p));
@@ -322,7 +343,7 @@ struct Builder {
             p.Cout = Cout; p.CoutT = Cout;
         }
         p.in = in;
-        p.w = W<bf16>(role + ".w");
+        p.w = W<f16>(role + ".w");
         p.bias = W<float>(role + ".b");
         p.residual = residual;
         p.post_add = post_add;
@@ -330,6 +351,11 @@ struct Builder {
         p.act = act;
         p.out = out;
         if (err) return;
+        {
+            const double M = (double)B * p.Ho * p.Wo, Nn = p.Cout, K = (double)R * R * Cin;
+            ops.meta(role, h->cfg.debug_simt_conv ? "conv_simt" : "conv_tc", 2.0 * M * Nn * K,
+                     2.0 * ((double)B * Hi * Wi * Cin + M * Nn * (residual ? 2 : 1) + Nn * K));
+        }
         if (h->cfg.debug_simt_conv) {
             ops.push_back([pl](cudaStream_t st) { return conv_launch_simt(pl->p, st); });
         } else {
@@ -339,26 +365,29 @@ struct Builder {
     }
 
     // scratch shared by all attention blocks (they run one after another)
-    bf16 *s_xn = nullptr, *s_qkv = nullptr, *s_ao = nullptr, *s_h1 = nullptr, *s_mid = nullptr;
+    f16 *s_xn = nullptr, *s_qkv = nullptr, *s_ao = nullptr, *s_h1 = nullptr, *s_mid = nullptr;
 
     // ImageSelfAttention (+ optional FF tail) on tokens x [B, hw*hw, C]; final_act applies to the block output.
-    void attention(const bf16* x, int hw, int C, const std::string& role, bf16* out, int final_act) {
+    void attention(const f16* x, int hw, int C, const std::string& role, f16* out, int final_act) {
         const int rows = B * hw * hw, L = hw * hw, heads = h->cfg.n_heads;
         const float* g = W<float>(role + ".ln.g");
         const float* b = W<float>(role + ".ln.b");
-        bf16 *xn = s_xn, *qkv = s_qkv, *ao = s_ao;
+        f16 *xn = s_xn, *qkv = s_qkv, *ao = s_ao;
         const int Bc = B;
+        ops.meta(role + ".ln", "layernorm", 0, 4.0 * rows * C);
         ops.push_back([=](cudaStream_t st) { return layernorm_launch(x, g, b, xn, rows, C, st); });
         conv(xn, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkv", nullptr, nullptr, 0, 0);
+        ops.meta(role + ".sdpa", "flash_attn", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
         ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
         if (!h->cfg.attn_ff) {
             conv(ao, hw, hw, C, out, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, final_act);
         } else {
-            bf16* mid = s_mid;
-            bf16* h1 = s_h1;
+            f16* mid = s_mid;
+            f16* h1 = s_h1;
             conv(ao, hw, hw, C, mid, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, 0);
             const float* g2 = W<float>(role + ".ffln.g");
             const float* b2 = W<float>(role + ".ffln.b");
+            ops.meta(role + ".ffln", "layernorm", 0, 4.0 * rows * C);
             ops.push_back([=](cudaStream_t st) { return layernorm_launch(mid, g2, b2, xn, rows, C, st); });
             conv(xn, hw, hw, C, h1, C, 1, 1, 0, false, role + ".ff1", nullptr, nullptr, 0, 2);
             conv(h1, hw, hw, C, out, C, 1, 1, 0, false, role + ".ff2", mid, nullptr, 0, final_act);
@@ -370,20 +399,30 @@ struct Builder {
         h->stats_floats += (size_t)B * C * 2;
         return p;
     }
-    void plane_stats(const bf16* x, int hw, int C, float* st) {
+    void plane_stats(const f16* x, int hw, int C, float* st) {
         const int HW = hw * hw, Bc = B;
-        int ppc = 256;  // pixels per CTA
+        const int ppc = 256;  // pixels per CTA
+        const int nslab = (HW + ppc - 1) / ppc, ngrp = C / 64;
+        float* partial = nullptr;
+        unsigned int* counters = nullptr;
+        if (h->alloc(&partial, (size_t)B * ngrp * nslab * 128) != 0 || h->alloc(&counters, (size_t)B * ngrp) != 0) {
+            err = -2;
+            return;
+        }
+        if (cudaMemset(counters, 0, (size_t)B * ngrp * sizeof(unsigned int)) != cudaSuccess) err = -2;
+        ops.meta("in_stats", "plane_stats", 0, 2.0 * B * HW * C);
         ops.push_back([=](cudaStream_t s) {
-            dim3 grid((HW + ppc - 1) / ppc, C / 64, Bc);
-            plane_stats_kernel<<<grid, 256, 0, s>>>(x, st, HW, C, ppc);
+            dim3 grid(nslab, ngrp, Bc);
+            plane_stats_kernel<<<grid, 256, 0, s>>>(x, partial, counters, st, HW, C, ppc);
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
     }
-    void instnorm_apply(const bf16* x, const float* st, const bf16* skip, const float* vec, int vec_stride, bf16* y, int hw,
+    void instnorm_apply(const f16* x, const float* st, const f16* skip, const float* vec, int vec_stride, f16* y, int hw,
                         int C) {
         const int HW = hw * hw;
         const size_t total8 = (size_t)B * HW * C / 8;
+        ops.meta("in_apply", "instnorm_apply", 0, 2.0 * B * HW * C * (skip ? 3 : 2));
         ops.push_back([=](cudaStream_t s) {
             int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
             instnorm_apply_kernel<<<blocks, 256, 0, s>>>(x, st, skip, vec, vec_stride, y, HW, C, total8);
@@ -403,7 +442,7 @@ static int build_program_r(Handle* h, int B) {
     const b2d_config& c = h->cfg;
     const int H = c.img_size;
     const int s[6] = {H, H / 2, H / 4, H / 8, H / 16, H / 32};
-    std::vector<Op> ops;
+    OpList ops;
     Builder bd(h, B, ops);
     h->stats_floats = 0;
     // scratch for attention (largest layer: fmap1 / dec3, rows = B*s1^2, C = 64; deeper layers are never larger)
@@ -427,6 +466,7 @@ static int build_program_r(Handle* h, int B) {
         const float* dd = bd.W<float>("dec_div");
         const float* tw = bd.W<float>("temb.w");
         const float* tb = bd.W<float>("temb.b");
+        ops.meta("temb", "temb_project", 2.0 * B * TS * 256, 4.0 * TS * 256);
         ops.push_back([=](cudaStream_t st) {
             temb_project_kernel<<<B, 256, 0, st>>>(hh->d_t, hh->has_y ? hh->d_y : nullptr, label, ei, dd, tw, tb, temb, 1024,
                                                    TS);
@@ -435,12 +475,14 @@ static int build_program_r(Handle* h, int B) {
         });
     }
     // ---- Encoder.forward (modules_DANRA_conditional.py:213-312)
-    bf16* f1_pre = bd.act((size_t)B * s[1] * s[1] * 64);
+    f16* f1_pre = bd.act((size_t)B * s[1] * s[1] * 64);
     {
         Handle* hh = h;
         const float* sw = bd.W<float>("stem.w");
         const int cin_total = c.c_hr + c.has_lsm + c.has_topo + c.cond_channels;
         const int chr = c.c_hr, Hh = H, ho = s[1];
+        ops.meta("conv1", "stem_conv", 2.0 * B * ho * ho * 64 * 64 * chr,
+                 (double)B * (4.0 * chr * Hh * Hh + ho * ho * 64 * (2 + 4)));
         ops.push_back([=](cudaStream_t st) {
             dim3 grid(ho / 8, ho / 8, B);
             const bool have_cond = (cin_total > chr);
@@ -451,13 +493,13 @@ static int build_program_r(Handle* h, int B) {
             return 0;
         });
     }
-    bf16* fmap[5];
+    f16* fmap[5];
     fmap[0] = bd.act((size_t)B * s[1] * s[1] * 64);
     bd.attention(f1_pre, s[1], 64, "ea0", fmap[0], 0);
     h->taps["f1_pre"] = {f1_pre, 64, s[1]};
     h->taps["fmap1"] = {fmap[0], 64, s[1]};
     // conv2 -> bn1 -> relu (:269-273)
-    bf16* cur = bd.act((size_t)B * s[2] * s[2] * 64);
+    f16* cur = bd.act((size_t)B * s[2] * s[2] * 64);
     bd.conv(fmap[0], s[1], s[1], 64, cur, 64, 8, 2, 3, false, "conv2", nullptr, nullptr, 0, 1);
     int cin = 64;
     for (int li = 1; li <= 4; ++li) {
@@ -466,14 +508,14 @@ static int build_program_r(Handle* h, int B) {
         const int hout = s[li + 1];
         const size_t n_out = (size_t)B * hout * hout * cout;
         const std::string r0 = "l" + std::to_string(li) + "b0", r1 = "l" + std::to_string(li) + "b1";
-        bf16* t1 = bd.act(n_out);
-        bf16* b0 = bd.act(n_out);
-        bf16* pre = bd.act(n_out);
-        const bf16* identity = cur;
+        f16* t1 = bd.act(n_out);
+        f16* b0 = bd.act(n_out);
+        f16* pre = bd.act(n_out);
+        const f16* identity = cur;
         const int stride = (li > 1) ? 2 : 1;
         bd.conv(cur, hin, hin, cin, t1, cout, 3, stride, 1, false, r0 + ".c1", nullptr, nullptr, 0, 1);
         if (li > 1) {
-            bf16* ds = bd.act(n_out);
+            f16* ds = bd.act(n_out);
             bd.conv(cur, hin, hin, cin, ds, cout, 1, 2, 0, false, r0 + ".ds", nullptr, nullptr, 0, 0);
             identity = ds;
         }
@@ -489,23 +531,23 @@ static int build_program_r(Handle* h, int B) {
         cin = cout;
     }
     // ---- Decoder.forward (:512-536), DecoderBlock.forward (:425-460)
-    const bf16* dcur = fmap[4];
+    const f16* dcur = fmap[4];
     for (int i = 0; i < 4; ++i) {
         const int ci = DEC_IN[i], co = DEC_OUT[i];
         const int hin = s[5 - i], hout = s[4 - i];
         const std::string r = "d" + std::to_string(i);
-        bf16* up = bd.act((size_t)B * hout * hout * ci);
+        f16* up = bd.act((size_t)B * hout * hout * ci);
         bd.conv(dcur, hin, hin, ci, up, ci, 1, 1, 0, true, r + ".up", nullptr, nullptr, 0, 0);
         float* st1 = bd.stats_slice(ci);
         bd.plane_stats(up, hout, ci, st1);
         bd.instnorm_apply(up, st1, nullptr, nullptr, 0, up, hout, ci);
-        bf16* cv = bd.act((size_t)B * hout * hout * co);
+        f16* cv = bd.act((size_t)B * hout * hout * co);
         bd.conv(up, hout, hout, ci, cv, co, 3, 1, 1, false, r + ".conv", nullptr, nullptr, 0, 0);
         float* st2 = bd.stats_slice(co);
         bd.plane_stats(cv, hout, co, st2);
-        bf16* pre = bd.act((size_t)B * hout * hout * co);
+        f16* pre = bd.act((size_t)B * hout * hout * co);
         bd.instnorm_apply(cv, st2, fmap[3 - i], temb + TEMB_DEC_OFF[i], TS, pre, hout, co);
-        bf16* dout = bd.act((size_t)B * hout * hout * co);
+        f16* dout = bd.act((size_t)B * hout * hout * co);
         bd.attention(pre, hout, co, "da" + std::to_string(i), dout, 1 /*ReLU after attention, :459*/);
         h->taps["dec" + std::to_string(i) + "_pre"] = {pre, co, hout};
         h->taps["dec" + std::to_string(i)] = {dout, co, hout};
@@ -513,7 +555,7 @@ static int build_program_r(Handle* h, int B) {
     }
     // ---- final_layer: ConvT -> IN -> Conv3x3(64->c_out), no skip/time/attention/activation (:503-509, :535)
     {
-        bf16* up = bd.act((size_t)B * H * H * 64);
+        f16* up = bd.act((size_t)B * H * H * 64);
         bd.conv(dcur, s[1], s[1], 64, up, 64, 1, 1, 0, true, "final.up", nullptr, nullptr, 0, 0);
         float* st = bd.stats_slice(64);
         bd.plane_stats(up, H, 64, st);
@@ -521,6 +563,7 @@ static int build_program_r(Handle* h, int B) {
         const float* tw = bd.W<float>("tail.w");
         const float* tb = bd.W<float>("tail.b");
         const int cout = c.c_out, Hh = H;
+        ops.meta("final.conv", "tail_conv", 2.0 * B * Hh * Hh * 576 * cout, (double)B * Hh * Hh * (64 * 2 + 4 * cout));
         ops.push_back([=](cudaStream_t s2) {
             dim3 grid((Hh + 31) / 32, (Hh + 7) / 8, B);
             tail_conv_kernel<<<grid, 256, 0, s2>>>(up, st, tw, tb, hh->cur_eps, Hh, Hh, cout);
@@ -530,7 +573,7 @@ static int build_program_r(Handle* h, int B) {
     }
     if (bd.err) return g_status.code ? g_status.code : fail(-1, "program build failed");
     if (h->stats_floats > STATS_CAPACITY_PER_SAMPLE * (size_t)c.max_batch) return fail(-1, "internal: stats buffer too small");
-    h->step_ops.swap(ops);
+    h->step_ops.swap(ops.v);
     h->prog_B = B;
     return 0;
 }
@@ -552,7 +595,6 @@ static int ensure_program(Handle* h, int B) {
 }
 
 static int run_step_ops(Handle* h, cudaStream_t st) {
-    if (h->stats_floats) B2D_CUDA(cudaMemsetAsync(h->d_stats, 0, h->stats_floats * sizeof(float), st));
     static const bool dbg = getenv("B2D_DEBUG_SYNC") != nullptr;
     int idx = 0;
     for (auto& op : h->step_ops) {
@@ -722,7 +764,7 @@ int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps
     h->cur_x = x;
     h->cur_eps = eps_out;
     B2D_TRY(run_step_ops(h, st));
-    h->last_launches = (int64_t)h->step_ops.size() + 1;
+    h->last_launches = (int64_t)h->step_ops.size();
     return 0;
 }
 
@@ -836,6 +878,49 @@ int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, c
 
 int64_t b2d_last_launch_count(const b2d_handle* h) { return h ? h->last_launches : 0; }
 
+int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32_t B, int32_t reps, b2d_op_profile* out,
+                     int32_t max_ops, int32_t* n_ops) {
+    B2D_CHECK(h && x && t_host && out && n_ops && reps >= 1, "bad argument");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = h->own_stream;
+    std::vector<int> ti(B);
+    for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
+    B2D_CUDA(cudaMemcpy(h->d_t, ti.data(), B * 4, cudaMemcpyHostToDevice));
+    h->cur_x = x;
+    h->cur_eps = h->d_eps;
+    const int n = (int)h->step_ops.size();
+    B2D_CHECK(n <= max_ops, "profile buffer too small");
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) B2D_CUDA(cudaEventCreate(&e));
+    std::vector<double> ms(n, 0.0);
+    for (int r = 0; r < reps + 1; ++r) {   // first repetition is a warm-up
+        B2D_CUDA(cudaEventRecord(ev[0], st));
+        for (int i = 0; i < n; ++i) {
+            B2D_TRY(h->step_ops[i](st));
+            B2D_CUDA(cudaEventRecord(ev[i + 1], st));
+        }
+        B2D_CUDA(cudaStreamSynchronize(st));
+        if (r == 0) continue;
+        for (int i = 0; i < n; ++i) {
+            float m = 0;
+            cudaEventElapsedTime(&m, ev[i], ev[i + 1]);
+            ms[i] += m;
+        }
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    for (int i = 0; i < n; ++i) {
+        const Op& op = h->step_ops[i];
+        memset(&out[i], 0, sizeof(out[i]));
+        strncpy(out[i].name, op.name.c_str(), sizeof(out[i].name) - 1);
+        strncpy(out[i].klass, op.klass.c_str(), sizeof(out[i].klass) - 1);
+        out[i].flops = op.flops;
+        out[i].bytes = op.bytes;
+        out[i].ms = ms[i] / reps;
+    }
+    *n_ops = n;
+    return 0;
+}
+
 int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out) {
     B2D_CHECK(h && name && out_host, "null argument");
     auto it = h->taps.find(name);
@@ -846,8 +931,9 @@ int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max
     B2D_CUDA(cudaDeviceSynchronize());
     B2D_CUDA(cudaMemcpy(tmp.data(), it->second.p, n * 2, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < n; ++i) {
-        uint32_t u = (uint32_t)tmp[i] << 16;
-        memcpy(&out_host[i], &u, 4);
+        __half hv;
+        memcpy(&hv, &tmp[i], 2);
+        out_host[i] = __half2float(hv);
     }
     if (C_out) *C_out = it->second.C;
     if (hw_out) *hw_out = it->second.hw;
@@ -871,8 +957,8 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
         p.Wo = (Wi + 2 * pad - S) / stride + 1;
         p.Cout = Cout; p.CoutT = Cout;
     }
-    p.in = (const bf16*)in; p.w = (const bf16*)w; p.bias = bias; p.residual = (const bf16*)residual;
-    p.post_add = post_add; p.post_stride = post_stride; p.act = act; p.out = (bf16*)out;
+    p.in = (const f16*)in; p.w = (const f16*)w; p.bias = bias; p.residual = (const f16*)residual;
+    p.post_add = post_add; p.post_stride = post_stride; p.act = act; p.out = (f16*)out;
     if (impl == 1) return conv_launch_simt(p, as_stream(stream));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -883,26 +969,37 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
 }
 
 int b2d_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t C, void* stream) {
-    return layernorm_launch((const bf16*)x, gamma, beta, (bf16*)y, rows, C, as_stream(stream));
+    return layernorm_launch((const f16*)x, gamma, beta, (f16*)y, rows, C, as_stream(stream));
 }
 
 int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream) {
     B2D_TRY(flash_attn_init_attrs());
-    return flash_attn_launch((const bf16*)qkv, (bf16*)o, B, L, C, heads, as_stream(stream));
+    return flash_attn_launch((const f16*)qkv, (f16*)o, B, L, C, heads, as_stream(stream));
 }
 
 int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t vec_stride, void* y, float* stats_ws,
                     int32_t B, int32_t HW, int32_t C, void* stream) {
     cudaStream_t st = as_stream(stream);
+    (void)stats_ws;  // kept for ABI stability; the operator owns its scratch
     B2D_CHECK(C % 64 == 0, "C must be a multiple of 64");
-    B2D_CUDA(cudaMemsetAsync(stats_ws, 0, (size_t)B * C * 2 * sizeof(float), st));
-    dim3 grid((HW + 255) / 256, C / 64, B);
-    plane_stats_kernel<<<grid, 256, 0, st>>>((const bf16*)x, stats_ws, HW, C, 256);
+    const int nslab = (HW + 255) / 256, ngrp = C / 64;
+    float* ws = nullptr;
+    const size_t n_stats = (size_t)B * C * 2, n_part = (size_t)B * ngrp * nslab * 128, n_cnt = (size_t)B * ngrp;
+    B2D_CUDA(cudaMalloc(&ws, (n_stats + n_part + n_cnt) * 4));
+    float* stats = ws;
+    float* partial = ws + n_stats;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n_stats + n_part);
+    cudaMemsetAsync(counters, 0, n_cnt * 4, st);
+    dim3 grid(nslab, ngrp, B);
+    plane_stats_kernel<<<grid, 256, 0, st>>>((const f16*)x, partial, counters, stats, HW, C, 256);
     const size_t total8 = (size_t)B * HW * C / 8;
     const int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
-    instnorm_apply_kernel<<<blocks, 256, 0, st>>>((const bf16*)x, stats_ws, (const bf16*)skip, vec, vec_stride, (bf16*)y, HW,
-                                                  C, total8);
-    B2D_CUDA(cudaGetLastError());
+    instnorm_apply_kernel<<<blocks, 256, 0, st>>>((const f16*)x, stats, (const f16*)skip, vec, vec_stride, (f16*)y, HW, C,
+                                                  total8);
+    cudaError_t e = cudaGetLastError();
+    cudaStreamSynchronize(st);
+    cudaFree(ws);
+    B2D_CUDA(e);
     return 0;
 }
 

@@ -1,15 +1,15 @@
 // Common device/host helpers for the b200ddpm kernels (sm_100a only).
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <cstdio>
 #include <string>
 
-typedef __nv_bfloat16 bf16;
-typedef __nv_bfloat162 bf162;
+typedef __half f16;
+typedef __half2 f162;
 
 namespace b2d {
 
@@ -55,13 +55,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    bf162 v = __floats2bfloat162_rn(a, b);
+// fp32 -> fp16 pair, saturating at +-65504 so that an out-of-range activation can never become inf/NaN
+constexpr float F16_MAX = 65504.0f;
+__device__ __forceinline__ float sat_h(float a) { return fminf(fmaxf(a, -F16_MAX), F16_MAX); }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    f162 v = __floats2half2_rn(sat_h(a), sat_h(b));
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
-    bf162 v = *reinterpret_cast<bf162*>(&u);
-    return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+    f162 v = *reinterpret_cast<f162*>(&u);
+    return __half22float2(v);
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -136,8 +139,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate, issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem], f16 inputs, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -168,7 +171,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 64 bf16 (=128 B), 8-row atoms 1024 B apart.
+// UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 64 f16 (=128 B), 8-row atoms 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 @[0,14), LBO>>4 @[16,30), SBO>>4 @[32,46), version=1 @[46,48), layout=2 @[61,64))
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
@@ -178,15 +181,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+// Instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M x N tile.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- legacy tensor-core + async-copy helpers (attention)
-__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void mma_f16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }

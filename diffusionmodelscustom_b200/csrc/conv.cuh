@@ -1,12 +1,12 @@
 // Implicit-GEMM convolution / projection kernels.
 //
-//   conv_tc_kernel   : tcgen05.mma (UMMA 128 x BN x 16, bf16 -> fp32 in TMEM), operands staged by TMA into
+//   conv_tc_kernel   : tcgen05.mma (UMMA 128 x BN x 16, f16 -> fp32 in TMEM), operands staged by TMA into
 //                      128B-swizzled K-major shared-memory tiles, warp-specialised (TMA / MMA / 4 epilogue warps),
 //                      mbarrier pipeline.  One 128-pixel x BN-channel output tile per CTA.
 //   conv_simt_kernel : one-thread-per-output CUDA-core restatement with the same epilogue; bring-up / unit-test
 //                      cross-check only (selected explicitly through b2d_op_conv2d(impl=1) or the debug flag).
 //
-// Activations are NHWC bf16.  Weights are packed [Cout][R*S*Cin] (tap-major, Cin innermost, K-major for UMMA).
+// Activations are NHWC f16.  Weights are packed [Cout][R*S*Cin] (tap-major, Cin innermost, K-major for UMMA).
 // GEMM view: M = B*Ho*Wo output pixels, N = Cout, K = R*S*Cin; K-blocks of 64 = one 128-byte swizzle row.
 //   * stride 1: the A tile of tap (r,s) is a shifted 4-D TMA box (64ch, TW, TH, TN) of the input; the zero padding is
 //     TMA out-of-bounds fill (signed start coordinates).
@@ -14,7 +14,7 @@
 //     and the box is again dense -> 5-D TMA.
 //   * ConvTranspose2d(k=2,s=2) is the GEMM [B*h*w, Cin] x [Cin, 4*Cout] with a pixel-shuffle store
 //     (SURVEY.md App. A); packed weight rows are (a*2+b)*Cout + co.
-// Epilogue (per output element): v = acc + bias[c]; v += residual; v = act(v); v += post_add[b][c]; store bf16.
+// Epilogue (per output element): v = acc + bias[c]; v += residual; v = act(v); v += post_add[b][c]; store f16.
 #pragma once
 #include "common.cuh"
 
@@ -30,14 +30,14 @@ struct ConvParams {
     int TW, TH, TN, tiles_w, tiles_h;
     // epilogue
     const float* bias;
-    const bf16* residual;
+    const f16* residual;
     const float* post_add;
     int post_stride;
     int act;  // 0 none, 1 relu, 2 gelu(erf)
-    bf16* out;
+    f16* out;
     // simt only
-    const bf16* in;
-    const bf16* w;
+    const f16* in;
+    const f16* w;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
     } else if (warp == 1) {
         // ===================== MMA issuer (one lane) =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+            constexpr uint32_t idesc = umma_idesc_f16(128, BN);
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                 const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * (BN * 128)));
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    // advance 16 bf16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    umma_bf16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    // advance 16 f16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    umma_f16(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
                 }
                 umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
                 if (++stage == STAGES) {
@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                     for (int j = 0; j < 4; ++j) {
                         const uint4 r4 = __ldg(rp + j);
                         float2 t;
-                        t = unpack_bf16(r4.x); f[j * 8 + 0] += t.x; f[j * 8 + 1] += t.y;
-                        t = unpack_bf16(r4.y); f[j * 8 + 2] += t.x; f[j * 8 + 3] += t.y;
-                        t = unpack_bf16(r4.z); f[j * 8 + 4] += t.x; f[j * 8 + 5] += t.y;
-                        t = unpack_bf16(r4.w); f[j * 8 + 6] += t.x; f[j * 8 + 7] += t.y;
+                        t = unpack_h2(r4.x); f[j * 8 + 0] += t.x; f[j * 8 + 1] += t.y;
+                        t = unpack_h2(r4.y); f[j * 8 + 2] += t.x; f[j * 8 + 3] += t.y;
+                        t = unpack_h2(r4.z); f[j * 8 + 4] += t.x; f[j * 8 + 5] += t.y;
+                        t = unpack_h2(r4.w); f[j * 8 + 6] += t.x; f[j * 8 + 7] += t.y;
                     }
                 }
                 if (p.act) {
@@ -230,10 +230,10 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 o;
-                    o.x = pack_bf16(f[j * 8 + 0], f[j * 8 + 1]);
-                    o.y = pack_bf16(f[j * 8 + 2], f[j * 8 + 3]);
-                    o.z = pack_bf16(f[j * 8 + 4], f[j * 8 + 5]);
-                    o.w = pack_bf16(f[j * 8 + 6], f[j * 8 + 7]);
+                    o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
+                    o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
+                    o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
+                    o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
                     op[j] = o;
                 }
             }
@@ -258,7 +258,7 @@ __global__ void conv_simt_kernel(const ConvParams p) {
         const int h = (int)(m % p.Ho);
         const int n = (int)(m / p.Ho);
         const int K = p.R * p.S * p.Cin;
-        const bf16* wrow = p.w + (size_t)co * K;
+        const f16* wrow = p.w + (size_t)co * K;
         float acc = 0.0f;
         for (int r = 0; r < p.R; ++r) {
             const int hi = h * p.stride + r - p.pad;
@@ -266,11 +266,11 @@ __global__ void conv_simt_kernel(const ConvParams p) {
             for (int s = 0; s < p.S; ++s) {
                 const int wi = w * p.stride + s - p.pad;
                 if (wi < 0 || wi >= p.Wi) continue;
-                const bf16* ip = p.in + (((size_t)n * p.Hi + hi) * p.Wi + wi) * p.Cin;
-                const bf16* wp = wrow + (r * p.S + s) * p.Cin;
+                const f16* ip = p.in + (((size_t)n * p.Hi + hi) * p.Wi + wi) * p.Cin;
+                const f16* wp = wrow + (r * p.S + s) * p.Cin;
                 for (int c = 0; c < p.Cin; c += 2) {
-                    const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(ip + c));
-                    const float2 b = __bfloat1622float2(*reinterpret_cast<const bf162*>(wp + c));
+                    const float2 a = __half22float2(*reinterpret_cast<const f162*>(ip + c));
+                    const float2 b = __half22float2(*reinterpret_cast<const f162*>(wp + c));
                     acc = fmaf(a.x, b.x, acc);
                     acc = fmaf(a.y, b.y, acc);
                 }
@@ -289,10 +289,10 @@ __global__ void conv_simt_kernel(const ConvParams p) {
         const size_t o = pix * p.CoutT + c;
         float v = acc;
         if (p.bias) v += p.bias[c];
-        if (p.residual) v += __bfloat162float(p.residual[o]);
+        if (p.residual) v += __half2float(p.residual[o]);
         v = apply_act(v, p.act);
         if (p.post_add) v += p.post_add[(size_t)n * p.post_stride + c];
-        p.out[o] = __float2bfloat16(v);
+        p.out[o] = __float2half_rn(sat_h(v));
     }
 }
 
@@ -313,7 +313,7 @@ inline PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
+inline int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
                           const uint32_t* box) {
     PFN_encodeTiled fn = get_encode_fn();
     B2D_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
@@ -325,7 +325,7 @@ inline int make_tmap_bf16(CUtensorMap* tm, const void* base, int rank, const uin
         es[i] = 1;
         if (i < rank - 1) gs[i] = strides_b[i];
     }
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B2D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -367,18 +367,18 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
         uint64_t dims[4] = {C, W, H, B};
         uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
         uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-        B2D_TRY(make_tmap_bf16(&pl.tmA, p.in, 4, dims, str, box));
+        B2D_TRY(make_tmap_f16(&pl.tmA, p.in, 4, dims, str, box));
     } else {
         uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, B};
         uint64_t str[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
         uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, (uint32_t)p.TN};
-        B2D_TRY(make_tmap_bf16(&pl.tmA, p.in, 5, dims, str, box));
+        B2D_TRY(make_tmap_f16(&pl.tmA, p.in, 5, dims, str, box));
     }
     const uint64_t K = (uint64_t)p.R * p.S * p.Cin;
     uint64_t wd[2] = {K, (uint64_t)p.Cout};
     uint64_t ws[1] = {K * 2};
     uint32_t wb[2] = {64, (uint32_t)bn};
-    B2D_TRY(make_tmap_bf16(&pl.tmB, p.w, 2, wd, ws, wb));
+    B2D_TRY(make_tmap_f16(&pl.tmB, p.w, 2, wd, ws, wb));
     pl.tc_ready = true;
     return 0;
 }

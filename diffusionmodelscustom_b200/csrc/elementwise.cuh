@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
 // ------------------------------------------------------------------------------------------------ stem convolution
 // Direct KSxKS / stride / pad convolution of an fp32 NCHW tensor with few channels (the diffusion state x, or the
 // step-invariant conditioning stack) to 64 channels, NHWC output.  FP32 FMA: K = KS*KS*Cx is tiny and the state must
-// not be rounded to bf16 before its first use.
+// not be rounded to f16 before its first use.
 //   out[b,ho,wo,co] = sum_{c,r,s} in[b,c,ho*st+r-pad,wo*st+s-pad] * w[co][c][r][s] (+ add[b,ho,wo,co]) (+ vec[b][co])
 // Encoder.conv1 (modules_DANRA_conditional.py:178-183, :260) is linear in its input channels, so the conditioning
 // channels' contribution is computed once per sampling job (out_f32) and added each step through `add`.
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
                                                         int w_coffset,                // first weight channel used
                                                         const float* __restrict__ add,  // [B,Ho,Wo,64] fp32 or null
                                                         const float* __restrict__ vec, int vec_stride,  // [B][..] or null
-                                                        bf16* __restrict__ out_bf16, float* __restrict__ out_f32, int Ho,
+                                                        f16* __restrict__ out_f16, float* __restrict__ out_f32, int Ho,
                                                         int Wo, int pad) {
     constexpr int PT = 8;                         // output tile side
     constexpr int IT = (PT - 1) * STRIDE + KS;    // input tile side
@@ -121,54 +121,76 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
         for (int i = 0; i < 16; ++i) out_f32[o + i] = acc[i];
     } else {
         uint4 v0, v1;
-        v0.x = pack_bf16(acc[0], acc[1]);   v0.y = pack_bf16(acc[2], acc[3]);
-        v0.z = pack_bf16(acc[4], acc[5]);   v0.w = pack_bf16(acc[6], acc[7]);
-        v1.x = pack_bf16(acc[8], acc[9]);   v1.y = pack_bf16(acc[10], acc[11]);
-        v1.z = pack_bf16(acc[12], acc[13]); v1.w = pack_bf16(acc[14], acc[15]);
-        uint4* op = reinterpret_cast<uint4*>(out_bf16 + o);
+        v0.x = pack_h2(acc[0], acc[1]);   v0.y = pack_h2(acc[2], acc[3]);
+        v0.z = pack_h2(acc[4], acc[5]);   v0.w = pack_h2(acc[6], acc[7]);
+        v1.x = pack_h2(acc[8], acc[9]);   v1.y = pack_h2(acc[10], acc[11]);
+        v1.z = pack_h2(acc[12], acc[13]); v1.w = pack_h2(acc[14], acc[15]);
+        uint4* op = reinterpret_cast<uint4*>(out_f16 + o);
         op[0] = v0;
         op[1] = v1;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
-// Statistics of an NHWC bf16 tensor per (sample, channel) plane: stats[b][c] = {sum, sum of squares} (fp32 atomics,
-// buffer zeroed at the start of the step).  CTA = 32 channel-pair lanes x 8 pixel lanes over a slab of pixels.
-__global__ void __launch_bounds__(256) plane_stats_kernel(const bf16* __restrict__ x, float* __restrict__ stats, int HW,
-                                                          int C, int pix_per_cta) {
+// Statistics of an NHWC f16 tensor per (sample, channel) plane -> stats[b][c] = {mean, rstd} (biased variance, eps 1e-5:
+// InstanceNorm2d defaults, modules_DANRA_conditional.py:409,417).  Deterministic two-level reduction without float
+// atomics: every CTA (32 channel-pair lanes x 8 pixel lanes over a slab of pixels) writes its partial {sum, sumsq};
+// the last CTA to arrive for a (sample, 64-channel group) adds the partials in slab order and publishes mean/rstd.
+__global__ void __launch_bounds__(256) plane_stats_kernel(const f16* __restrict__ x, float* __restrict__ partial,
+                                                          unsigned int* __restrict__ counters, float* __restrict__ stats,
+                                                          int HW, int C, int pix_per_cta) {
     __shared__ float s_sum[8][64], s_sq[8][64];
-    const int b = blockIdx.z;
-    const int c0 = blockIdx.y * 64;
+    __shared__ bool s_last;
+    const int b = blockIdx.z, grp = blockIdx.y, ngrp = gridDim.y, nslab = gridDim.x, slab = blockIdx.x;
+    const int c0 = grp * 64;
     const int cl = (threadIdx.x & 31) * 2, pl = threadIdx.x >> 5;
-    const int p0 = blockIdx.x * pix_per_cta;
+    const int p0 = slab * pix_per_cta;
     const int p1 = min(p0 + pix_per_cta, HW);
     float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
-    const bf16* xb = x + (size_t)b * HW * C + c0 + cl;
+    const f16* xb = x + (size_t)b * HW * C + c0 + cl;
     for (int p = p0 + pl; p < p1; p += 8) {
-        const float2 v = __bfloat1622float2(*reinterpret_cast<const bf162*>(xb + (size_t)p * C));
+        const float2 v = __half22float2(*reinterpret_cast<const f162*>(xb + (size_t)p * C));
         a0 += v.x; a1 += v.y;
         q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
     }
     s_sum[pl][cl] = a0; s_sum[pl][cl + 1] = a1;
     s_sq[pl][cl] = q0;  s_sq[pl][cl + 1] = q1;
     __syncthreads();
+    float* part = partial + ((size_t)(b * ngrp + grp) * nslab) * 128;
     if (threadIdx.x < 64) {
         float s = 0.f, q = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
-        float* st = stats + ((size_t)b * C + c0 + threadIdx.x) * 2;
-        atomicAdd(st, s);
-        atomicAdd(st + 1, q);
+        part[(size_t)slab * 128 + threadIdx.x] = s;
+        part[(size_t)slab * 128 + 64 + threadIdx.x] = q;
+        __threadfence();
     }
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&counters[b * ngrp + grp], 1u) == (unsigned)(nslab - 1));
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 64) {
+        float s = 0.f, q = 0.f;
+        for (int i = 0; i < nslab; ++i) {
+            s += __ldcg(part + (size_t)i * 128 + threadIdx.x);
+            q += __ldcg(part + (size_t)i * 128 + 64 + threadIdx.x);
+        }
+        const float inv = 1.0f / (float)HW;
+        const float mean = s * inv;
+        const float var = fmaxf(q * inv - mean * mean, 0.f);
+        float* st = stats + ((size_t)b * C + c0 + threadIdx.x) * 2;
+        st[0] = mean;
+        st[1] = rsqrtf(var + 1e-5f);
+    }
+    if (threadIdx.x == 0) counters[b * ngrp + grp] = 0u;  // self-resetting: no per-step memset
 }
 
-// y = (x - mean) * rstd (+ skip) (+ vec[b][c]); mean/rstd from stats (biased variance, eps 1e-5: InstanceNorm2d defaults,
-// modules_DANRA_conditional.py:409,417).  8 channels (16 B) per thread.
-__global__ void __launch_bounds__(256) instnorm_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
-                                                             const bf16* __restrict__ skip, const float* __restrict__ vec,
-                                                             int vec_stride, bf16* __restrict__ y, int HW, int C,
+// y = (x - mean) * rstd (+ skip) (+ vec[b][c]); stats[b][c] = {mean, rstd}.  8 channels (16 B) per thread.
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const f16* __restrict__ x, const float* __restrict__ stats,
+                                                             const f16* __restrict__ skip, const float* __restrict__ vec,
+                                                             int vec_stride, f16* __restrict__ y, int HW, int C,
                                                              size_t total_vec8) {
-    const float inv_hw = 1.0f / (float)HW;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec8; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 8;
         const int c = (int)(e % C);
@@ -176,23 +198,19 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const bf16* __restr
         const uint4 xv = *reinterpret_cast<const uint4*>(x + e);
         float f[8];
         float2 t;
-        t = unpack_bf16(xv.x); f[0] = t.x; f[1] = t.y;
-        t = unpack_bf16(xv.y); f[2] = t.x; f[3] = t.y;
-        t = unpack_bf16(xv.z); f[4] = t.x; f[5] = t.y;
-        t = unpack_bf16(xv.w); f[6] = t.x; f[7] = t.y;
+        t = unpack_h2(xv.x); f[0] = t.x; f[1] = t.y;
+        t = unpack_h2(xv.y); f[2] = t.x; f[3] = t.y;
+        t = unpack_h2(xv.z); f[4] = t.x; f[5] = t.y;
+        t = unpack_h2(xv.w); f[6] = t.x; f[7] = t.y;
         const float* st = stats + ((size_t)b * C + c) * 2;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float mean = st[2 * j] * inv_hw;
-            const float var = fmaxf(st[2 * j + 1] * inv_hw - mean * mean, 0.f);
-            f[j] = (f[j] - mean) * rsqrtf(var + 1e-5f);
-        }
+        for (int j = 0; j < 8; ++j) f[j] = (f[j] - st[2 * j]) * st[2 * j + 1];
         if (skip) {
             const uint4 sv = *reinterpret_cast<const uint4*>(skip + e);
-            t = unpack_bf16(sv.x); f[0] += t.x; f[1] += t.y;
-            t = unpack_bf16(sv.y); f[2] += t.x; f[3] += t.y;
-            t = unpack_bf16(sv.z); f[4] += t.x; f[5] += t.y;
-            t = unpack_bf16(sv.w); f[6] += t.x; f[7] += t.y;
+            t = unpack_h2(sv.x); f[0] += t.x; f[1] += t.y;
+            t = unpack_h2(sv.y); f[2] += t.x; f[3] += t.y;
+            t = unpack_h2(sv.z); f[4] += t.x; f[5] += t.y;
+            t = unpack_h2(sv.w); f[6] += t.x; f[7] += t.y;
         }
         if (vec) {
             const float* vp = vec + (size_t)b * vec_stride + c;
@@ -200,8 +218,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const bf16* __restr
             for (int j = 0; j < 8; ++j) f[j] += vp[j];
         }
         uint4 o;
-        o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-        o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+        o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
+        o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
         *reinterpret_cast<uint4*>(y + e) = o;
     }
 }
@@ -211,7 +229,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const bf16* __restr
 // result (eps_hat).  Cout is 1 (or a few): a 576-long reduction per pixel, not a GEMM.  The normalisation is applied on
 // the fly; zero padding applies to the *normalised* tensor, so out-of-image taps contribute nothing.
 // One warp per output pixel row segment: lane <-> channel pair; warp-reduce over 64 channels.
-__global__ void __launch_bounds__(256) tail_conv_kernel(const bf16* __restrict__ x,      // [B,H,W,64] (un-normalised)
+__global__ void __launch_bounds__(256) tail_conv_kernel(const f16* __restrict__ x,      // [B,H,W,64] (un-normalised)
                                                         const float* __restrict__ stats,  // [B][64][2]
                                                         const float* __restrict__ w,      // [c_out][64][3][3]
                                                         const float* __restrict__ bias, float* __restrict__ out,  // [B,c_out,H,W]
@@ -221,12 +239,9 @@ __global__ void __launch_bounds__(256) tail_conv_kernel(const bf16* __restrict__
     const int b = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x < 64) {
-        const float inv = 1.0f / (float)(H * W);
         const float* st = stats + ((size_t)b * 64 + threadIdx.x) * 2;
-        const float mean = st[0] * inv;
-        const float var = fmaxf(st[1] * inv - mean * mean, 0.f);
-        s_mean[threadIdx.x] = mean;
-        s_rstd[threadIdx.x] = rsqrtf(var + 1e-5f);
+        s_mean[threadIdx.x] = st[0];
+        s_rstd[threadIdx.x] = st[1];
     }
     for (int oc = 0; oc < c_out; ++oc) {
         __syncthreads();
@@ -252,8 +267,8 @@ __global__ void __launch_bounds__(256) tail_conv_kernel(const bf16* __restrict__
                     for (int s = 0; s < 3; ++s) {
                         const int wi = wcol + s - 1;
                         if (wi < 0 || wi >= W) continue;
-                        const float2 v = __bfloat1622float2(
-                            *reinterpret_cast<const bf162*>(x + (((size_t)b * H + hi) * W + wi) * 64 + c));
+                        const float2 v = __half22float2(
+                            *reinterpret_cast<const f162*>(x + (((size_t)b * H + hi) * W + wi) * 64 + c));
                         acc = fmaf((v.x - m0) * r0, s_w[r * 3 + s][c], acc);
                         acc = fmaf((v.y - m1) * r1, s_w[r * 3 + s][c + 1], acc);
                     }

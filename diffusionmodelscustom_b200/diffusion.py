@@ -105,6 +105,21 @@ class DiffusionUtils:
         return out
 
 
+    def sample_host(self, x: torch.Tensor, model: nn.Module, y=None, cond_img=None, lsm_cond=None, topo_cond=None, *,
+                    noise=None, seed: int = None, sample_offset: int = 0, device="cuda"):
+        """Same contract as ``sample`` with HOST tensors in and out — what the reference's generation scripts do around
+        the call (``x.to(device)`` … ``generated.detach().cpu()``, generation_DANRA_conditional.py:389-426) — as ONE native
+        call: pinned/pageable host buffers -> H2D -> graph-replayed loop -> D2H."""
+        if not isinstance(model, NativeModel):
+            raise TypeError("sample_host needs a native model (DiffusionNet / UNet_downscale of this package)")
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        model.eval()
+        return model.native_sample_host(x, y, cond_img, lsm_cond, topo_cond, self.betas, self.alphas, self.alpha_hat,
+                                        device, noise=noise, seed=seed, sample_offset=sample_offset,
+                                        noise_scale=0.005 if self.data_scaled else 1.0)
+
+
 class DiffusionUtilsV2(DiffusionUtils):
     def __init__(self, n_timesteps: int = 1000, beta_min: float = 1e-4, beta_max: float = 0.02, device: str = 'cpu',
                  scheduler: str = 'linear', img_size: int = 64, data_scaled: bool = False):

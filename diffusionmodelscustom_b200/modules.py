@@ -319,11 +319,7 @@ class DiffusionNet(NativeModel):
             raise N.NativeError("x must be a contiguous fp32 CUDA tensor")
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
-            skey = (betas.data_ptr(), int(betas._version), len(betas))
-            if skey != self._sched_key:
-                b, a, ah = (v.detach().to("cpu", torch.float32).contiguous() for v in (betas, alphas, alpha_hat))
-                N.check(N.lib().b2d_set_schedule(h, b.data_ptr(), a.data_ptr(), ah.data_ptr(), len(b)))
-                self._sched_key = skey
+            self._set_schedule(h, betas, alphas, alpha_hat)
             self._set_conditioning(h, B, y, cond_img, lsm_cond, topo_cond, stream)
             nz = self._f32c(noise, "noise")
             N.check(N.lib().b2d_sample(h, x.data_ptr(), N.ptr(nz), int(seed), int(sample_offset), float(noise_scale), B,
@@ -331,6 +327,58 @@ class DiffusionNet(NativeModel):
             if nz is not None:
                 torch.cuda.current_stream().synchronize()   # nz staging copy must outlive the queued work
         return x
+
+
+    def _set_schedule(self, h, betas, alphas, alpha_hat):
+        skey = (betas.data_ptr(), int(betas._version), len(betas))
+        if skey != self._sched_key:
+            b, a, ah = (v.detach().to("cpu", torch.float32).contiguous() for v in (betas, alphas, alpha_hat))
+            N.check(N.lib().b2d_set_schedule(h, b.data_ptr(), a.data_ptr(), ah.data_ptr(), len(b)))
+            self._sched_key = skey
+
+    @torch.no_grad()
+    def native_sample_host(self, x_host, y, cond_img, lsm_cond, topo_cond, betas, alphas, alpha_hat, device, noise=None,
+                           seed=0, sample_offset=0, noise_scale=1.0):
+        """End-to-end entry on HOST tensors (b2d_sample_host): H2D of x_T/conditioning, the whole loop, D2H of x_0."""
+        B, _, H, _ = x_host.shape
+        device = torch.device(device)
+        h = self._ensure(B, H, device)
+
+        def hostc(t, dt=torch.float32):
+            if t is None:
+                return None
+            if t.is_cuda:
+                raise ValueError("native_sample_host takes host tensors")
+            return t.detach().to(dt).contiguous()
+
+        out = hostc(x_host).clone()
+        e = self.encoder
+        lsm = hostc(lsm_cond) if hasattr(e, "lsm") else None
+        topo = hostc(topo_cond) if hasattr(e, "elevation") else None
+        cond, yy, nz = hostc(cond_img), hostc(y, torch.int64), hostc(noise)
+        with torch.cuda.device(device):
+            self._set_schedule(h, betas, alphas, alpha_hat)
+            self._cond_key = None   # conditioning of the handle is overwritten by this call
+            N.check(N.lib().b2d_sample_host(h, out.data_ptr(), N.ptr(lsm), N.ptr(topo), N.ptr(cond), 0, 0, N.ptr(yy),
+                                            N.ptr(nz), int(seed), int(sample_offset), float(noise_scale), B))
+        return out
+
+    @torch.no_grad()
+    def profile_step(self, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=None, reps=5):
+        """Per-launch device times of one eps evaluation (b2d_profile_step) as a list of dicts."""
+        B, _, H, _ = x.shape
+        h = self._ensure(B, H, x.device)
+        xx = self._f32c(x, "x")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._set_conditioning(h, B, y, cond_img, lsm_cond, topo_cond, stream)
+            torch.cuda.synchronize()
+            th = t.detach().to("cpu", torch.int64).contiguous()
+            buf = (N.OpProfile * 512)()
+            n = C.c_int32()
+            N.check(N.lib().b2d_profile_step(h, xx.data_ptr(), th.data_ptr(), B, reps, buf, 512, C.byref(n)))
+        return [dict(name=buf[i].name.decode(), klass=buf[i].klass.decode(), flops=buf[i].flops, bytes=buf[i].bytes,
+                     ms=buf[i].ms) for i in range(n.value)]
 
 
 # north_star alias: UNet(c_in, c_out, time_dim) style constructor over the same network

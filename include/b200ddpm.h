@@ -66,7 +66,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out);
 void b2d_destroy(b2d_handle* h);
 
 /* Replaces `model.load_state_dict(torch.load(p)['network_params'])` (generation_DANRA_conditional.py:354-360):
- * takes the reference's keys, folds eval-mode BatchNorm into the convolutions, re-packs to K-major bf16. */
+ * takes the reference's keys, folds eval-mode BatchNorm into the convolutions, re-packs to K-major f16. */
 int b2d_load_weights(b2d_handle* h, const b2d_tensor* tensors, int32_t n);
 
 /* Schedule tables owned by DiffusionUtils (diffusion_DANRA_conditional.py:47-51): T floats each, host memory. */
@@ -95,21 +95,34 @@ int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, c
 
 /* Kernel launches issued by the last b2d_forward / b2d_sample on this handle (graph nodes x replays). */
 int64_t b2d_last_launch_count(const b2d_handle* h);
-/* Bring-up aid: copies a named NHWC bf16 activation of the last evaluation ("fmap1".."fmap5", "dec0".."dec3", ...) to
+/* Per-launch device time of one eps evaluation: runs the step program `reps` times (after one warm-up) with a CUDA event
+ * between launches on the handle's stream and reports, per launch, its layer name, kernel class, algorithmic FLOPs/bytes
+ * and mean duration.  x: device fp32 [B,c_hr,H,W]; t_host: host int64 [B].  Used by bench.py for the live roofline. */
+typedef struct b2d_op_profile {
+    char name[48];
+    char klass[24];
+    double flops;
+    double bytes;
+    double ms;
+} b2d_op_profile;
+int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32_t B, int32_t reps, b2d_op_profile* out,
+                     int32_t max_ops, int32_t* n_ops);
+
+/* Bring-up aid: copies a named NHWC f16 activation of the last evaluation ("fmap1".."fmap5", "dec0".."dec3", ...) to
  * host fp32 [B,hw,hw,C]; synchronises the device. */
 int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out);
 
 /* ---- single operators (unit-test / profiling entry points; all pointers are device memory) ------------------ */
-/* NHWC bf16 convolution / projection through the same kernels the model uses.
- * w_packed: bf16 [Cout][R*S*Cin] (convt: [(a*2+b)*CoutT+co][Cin]); impl 0 = tcgen05, 1 = CUDA-core cross-check. */
-int b2d_op_conv2d(const void* in_bf16, const void* w_packed_bf16, const float* bias, const void* residual_bf16,
-                  const float* post_add, int32_t post_stride, void* out_bf16, int32_t B, int32_t Hi, int32_t Wi,
+/* NHWC f16 convolution / projection through the same kernels the model uses.
+ * w_packed: f16 [Cout][R*S*Cin] (convt: [(a*2+b)*CoutT+co][Cin]); impl 0 = tcgen05, 1 = CUDA-core cross-check. */
+int b2d_op_conv2d(const void* in_f16, const void* w_packed_f16, const float* bias, const void* residual_f16,
+                  const float* post_add, int32_t post_stride, void* out_f16, int32_t B, int32_t Hi, int32_t Wi,
                   int32_t Cin, int32_t Cout, int32_t R, int32_t S, int32_t stride, int32_t pad, int32_t convt,
                   int32_t act, int32_t impl, void* stream);
-int b2d_op_layernorm(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16, int32_t rows, int32_t C,
+int b2d_op_layernorm(const void* x_f16, const float* gamma, const float* beta, void* y_f16, int32_t rows, int32_t C,
                      void* stream);
-int b2d_op_attention(const void* qkv_bf16, void* o_bf16, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream);
-int b2d_op_instnorm(const void* x_bf16, const void* skip_bf16, const float* vec, int32_t vec_stride, void* y_bf16,
+int b2d_op_attention(const void* qkv_f16, void* o_f16, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream);
+int b2d_op_instnorm(const void* x_f16, const void* skip_f16, const float* vec, int32_t vec_stride, void* y_f16,
                     float* stats_ws, int32_t B, int32_t HW, int32_t C, void* stream);
 int b2d_op_posterior_update(float* x, const float* eps, const float* z_or_null, const float* betas, const float* alphas,
                             const float* alpha_hat, int32_t i, int32_t B, int64_t per_sample, uint64_t seed,

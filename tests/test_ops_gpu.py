@@ -1,7 +1,7 @@
 """GPU unit tests of every kernel class through the C ABI, against plain torch FP32 on the CPU.
 
-Inputs are rounded to bf16 first so the only differences are accumulation order and the bf16 rounding of the output
-(<= 2^-9 relative per element): tolerance 6e-3 relative L2 for bf16-output kernels, exact for the posterior update."""
+Inputs are rounded to f16 first so the only differences are accumulation order and the f16 rounding of the output
+(<= 2^-9 relative per element): tolerance 6e-3 relative L2 for f16-output kernels, exact for the posterior update."""
 import math
 
 import pytest
@@ -12,11 +12,11 @@ from diffusionmodelscustom_b200 import _native as N
 from tests import gpu_util as G
 
 pytestmark = pytest.mark.gpu
-TOL = 6e-3
+TOL = 1.5e-3
 
 
 def _bf(x):
-    return x.to(torch.bfloat16).float()
+    return x.to(torch.float16).float()
 
 
 CONV_CASES = [
@@ -45,7 +45,7 @@ def test_conv_matches_torch(case, impl):
     w = _bf(torch.randn(Cout, Cin, R, R, generator=g) / math.sqrt(Cin * R * R))
     bias = torch.randn(Cout, generator=g)
     ref = F.conv2d(x, w, bias, stride, pad)
-    out = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, R, stride, pad, impl=impl)
+    out = G.conv2d(G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, R, stride, pad, impl=impl)
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
 
 
@@ -60,11 +60,11 @@ def test_conv_full_epilogue(impl):
     res = _bf(torch.randn(B, C, H, H, generator=g))
     vec = torch.randn(B, 200, generator=g)   # stride 200, first C used
     ref = F.relu(F.conv2d(x, w, bias, 1, 1) + res) + vec[:, :C, None, None]
-    out = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), G.nhwc_bf16(res), vec.cuda(), B, H, H, C, C, 3, 1, 1,
+    out = G.conv2d(G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), G.nhwc_f16(res), vec.cuda(), B, H, H, C, C, 3, 1, 1,
                    act=1, impl=impl)
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
     ref2 = F.gelu(F.conv2d(x, w, bias, 1, 1))
-    out2 = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, C, C, 3, 1, 1, act=2, impl=impl)
+    out2 = G.conv2d(G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, C, C, 3, 1, 1, act=2, impl=impl)
     assert G.rel_l2(G.to_nchw_f32(out2), ref2) < TOL
 
 
@@ -77,7 +77,7 @@ def test_conv_transpose_matches_torch(shape, impl):
     w = _bf(torch.randn(C, C, 2, 2, generator=g) / math.sqrt(C))
     bias = torch.randn(C, generator=g)
     ref = F.conv_transpose2d(x, w, bias, stride=2)
-    out = G.conv2d(G.nhwc_bf16(x), G.pack_convt_weight(w), bias.cuda(), None, None, B, H, H, C, C, 1, 1, 0, convt=True, impl=impl)
+    out = G.conv2d(G.nhwc_f16(x), G.pack_convt_weight(w), bias.cuda(), None, None, B, H, H, C, C, 1, 1, 0, convt=True, impl=impl)
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
 
 
@@ -87,8 +87,8 @@ def test_layernorm(C):
     rows = 333
     x = _bf(torch.randn(rows, C, generator=g) * 3 + 1.5)
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
-    y = torch.empty(rows, C, dtype=torch.bfloat16, device="cuda")
-    xd, gd, bd = x.to(torch.bfloat16).cuda(), gamma.cuda(), beta.cuda()   # keep device copies alive across the call
+    y = torch.empty(rows, C, dtype=torch.float16, device="cuda")
+    xd, gd, bd = x.to(torch.float16).cuda(), gamma.cuda(), beta.cuda()   # keep device copies alive across the call
     N.check(N.lib().b2d_op_layernorm(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, C, G.stream()))
     torch.cuda.synchronize()
     assert G.rel_l2(y.float().cpu(), F.layer_norm(x, (C,), gamma, beta, 1e-5)) < TOL
@@ -106,11 +106,11 @@ def test_attention_matches_torch(case):
     qkv = _bf(torch.randn(B, L, 3 * C, generator=g))
     q, k, v = (t.reshape(B, L, heads, d).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1))
     ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(B, L, C)
-    o = torch.empty(B, L, C, dtype=torch.bfloat16, device="cuda")
-    qd = qkv.to(torch.bfloat16).cuda()
+    o = torch.empty(B, L, C, dtype=torch.float16, device="cuda")
+    qd = qkv.to(torch.float16).cuda()
     N.check(N.lib().b2d_op_attention(qd.data_ptr(), o.data_ptr(), B, L, C, heads, G.stream()))
     torch.cuda.synchronize()
-    assert G.rel_l2(o.float().cpu(), ref) < 1e-2     # P is rounded to bf16 before P.V
+    assert G.rel_l2(o.float().cpu(), ref) < 3e-3     # P is rounded to fp16 before P.V
 
 
 @pytest.mark.parametrize("shape", [(2, 16, 512), (3, 1024, 64), (1, 16384, 64), (4, 4, 256)])
@@ -123,9 +123,9 @@ def test_instance_norm_with_skip_and_vector(shape):
     mean = x.mean(1, keepdim=True)
     var = x.var(1, unbiased=False, keepdim=True)
     ref = (x - mean) / torch.sqrt(var + 1e-5) + skip + vec[:, None, :C]
-    y = torch.empty(B, HW, C, dtype=torch.bfloat16, device="cuda")
+    y = torch.empty(B, HW, C, dtype=torch.float16, device="cuda")
     ws = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
-    xd, sd, vd = x.to(torch.bfloat16).cuda(), skip.to(torch.bfloat16).cuda(), vec.cuda()
+    xd, sd, vd = x.to(torch.float16).cuda(), skip.to(torch.float16).cuda(), vec.cuda()
     N.check(N.lib().b2d_op_instnorm(xd.data_ptr(), sd.data_ptr(), vd.data_ptr(), C + 8, y.data_ptr(), ws.data_ptr(), B, HW, C,
                                     G.stream()))
     torch.cuda.synchronize()

@@ -16,7 +16,7 @@ from tests.model_util import build_ours_r, inputs_r   # noqa: E402
 
 
 def bf(x):
-    return x.to(torch.bfloat16).float()
+    return x.to(torch.float16).float()
 
 
 def try_(name, fn):
@@ -34,7 +34,7 @@ def conv_case(B, H, Cin, Cout, R, stride, pad, impl):
     w = bf(torch.randn(Cout, Cin, R, R, generator=g) / math.sqrt(Cin * R * R))
     bias = torch.randn(Cout, generator=g)
     ref = F.conv2d(x, w, bias, stride, pad)
-    out = G.conv2d(G.nhwc_bf16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, R, stride, pad, impl=impl)
+    out = G.conv2d(G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, R, stride, pad, impl=impl)
     return G.rel_l2(G.to_nchw_f32(out), ref)
 
 
