@@ -181,9 +181,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, M x N tile.
+// Instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor): c_format[4,6)=1 (F32 accumulate), a_format[7,10) =
+// b_format[10,13) = 0 (F16; 1 would be BF16), a/b_major = 0 (K-major), N>>3 @[17,23), M>>4 @[24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- legacy tensor-core + async-copy helpers (attention)

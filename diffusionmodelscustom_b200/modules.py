@@ -304,7 +304,7 @@ class DiffusionNet(NativeModel):
         with torch.cuda.device(x.device):
             stream = torch.cuda.current_stream().cuda_stream
             self._set_conditioning(h, B, y, cond_img, lsm_cond, topo_cond, stream)
-            out = torch.empty((B, self.decoder.output_channels, H, H), device=x.device, dtype=torch.float32)
+            out = torch.full((B, self.decoder.output_channels, H, H), float("nan"), device=x.device, dtype=torch.float32)
             th = t.detach().to("cpu", torch.int64).contiguous()
             N.check(N.lib().b2d_forward(h, xx.data_ptr(), th.data_ptr(), out.data_ptr(), B, stream))
         return out

@@ -11,7 +11,8 @@ def stream():
 def rel_l2(a, b):
     a = torch.as_tensor(a).double().cpu()
     b = torch.as_tensor(b).double().cpu()
-    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+    r = float((a - b).norm() / b.norm().clamp_min(1e-30))
+    return r if r == r else float("inf")   # NaN (unwritten / poisoned output) is an infinite error
 
 
 def nhwc_f16(x_nchw):
@@ -28,10 +29,10 @@ def pack_convt_weight(w):          # [Cin,Cout,2,2] -> f16 [(a*2+b)*Cout+co][ci]
 
 def conv2d(x_nhwc, w_packed, bias, residual, post_add, B, Hi, Wi, Cin, Cout, R, stride, pad, convt=False, act=0, impl=0):
     if convt:
-        out = torch.empty(B, 2 * Hi, 2 * Wi, Cout, dtype=torch.float16, device="cuda")
+        out = torch.full((B, 2 * Hi, 2 * Wi, Cout), float("nan"), dtype=torch.float16, device="cuda")
     else:
         Ho = (Hi + 2 * pad - R) // stride + 1
-        out = torch.empty(B, Ho, Ho, Cout, dtype=torch.float16, device="cuda")
+        out = torch.full((B, Ho, Ho, Cout), float("nan"), dtype=torch.float16, device="cuda")  # poison: stale memory must not pass
     N.check(N.lib().b2d_op_conv2d(x_nhwc.data_ptr(), w_packed.data_ptr(), N.ptr(bias), N.ptr(residual), N.ptr(post_add),
                                   0 if post_add is None else post_add.shape[1], out.data_ptr(), B, Hi, Wi, Cin, Cout, R, R,
                                   stride, pad, int(convt), act, impl, stream()))

@@ -87,7 +87,7 @@ def test_layernorm(C):
     rows = 333
     x = _bf(torch.randn(rows, C, generator=g) * 3 + 1.5)
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
-    y = torch.empty(rows, C, dtype=torch.float16, device="cuda")
+    y = torch.full((rows, C), float("nan"), dtype=torch.float16, device="cuda")
     xd, gd, bd = x.to(torch.float16).cuda(), gamma.cuda(), beta.cuda()   # keep device copies alive across the call
     N.check(N.lib().b2d_op_layernorm(xd.data_ptr(), gd.data_ptr(), bd.data_ptr(), y.data_ptr(), rows, C, G.stream()))
     torch.cuda.synchronize()
@@ -106,7 +106,7 @@ def test_attention_matches_torch(case):
     qkv = _bf(torch.randn(B, L, 3 * C, generator=g))
     q, k, v = (t.reshape(B, L, heads, d).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1))
     ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(B, L, C)
-    o = torch.empty(B, L, C, dtype=torch.float16, device="cuda")
+    o = torch.full((B, L, C), float("nan"), dtype=torch.float16, device="cuda")
     qd = qkv.to(torch.float16).cuda()
     N.check(N.lib().b2d_op_attention(qd.data_ptr(), o.data_ptr(), B, L, C, heads, G.stream()))
     torch.cuda.synchronize()
@@ -123,7 +123,7 @@ def test_instance_norm_with_skip_and_vector(shape):
     mean = x.mean(1, keepdim=True)
     var = x.var(1, unbiased=False, keepdim=True)
     ref = (x - mean) / torch.sqrt(var + 1e-5) + skip + vec[:, None, :C]
-    y = torch.empty(B, HW, C, dtype=torch.float16, device="cuda")
+    y = torch.full((B, HW, C), float("nan"), dtype=torch.float16, device="cuda")
     ws = torch.empty(B * C * 2, dtype=torch.float32, device="cuda")
     xd, sd, vd = x.to(torch.float16).cuda(), skip.to(torch.float16).cuda(), vec.cuda()
     N.check(N.lib().b2d_op_instnorm(xd.data_ptr(), sd.data_ptr(), vd.data_ptr(), C + 8, y.data_ptr(), ws.data_ptr(), B, HW, C,
