@@ -19,6 +19,8 @@ template <int C>
 __global__ void __launch_bounds__(256) layernorm_rows_kernel(const f16* __restrict__ x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, f16* __restrict__ y,
                                                              int rows) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int PER = C / 32;  // elements per lane (2..16), contiguous
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -55,10 +57,10 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const f16* __restri
 inline int layernorm_launch(const f16* x, const float* g, const float* b, f16* y, int rows, int C, cudaStream_t st) {
     const int blocks = (rows + 7) / 8;
     switch (C) {
-        case 64: layernorm_rows_kernel<64><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
-        case 128: layernorm_rows_kernel<128><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
-        case 256: layernorm_rows_kernel<256><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
-        case 512: layernorm_rows_kernel<512><<<blocks, 256, 0, st>>>(x, g, b, y, rows); break;
+        case 64: B2D_CUDA(launch_k(layernorm_rows_kernel<64>, dim3(blocks), dim3(256), 0, st, x, g, b, y, rows)); break;
+        case 128: B2D_CUDA(launch_k(layernorm_rows_kernel<128>, dim3(blocks), dim3(256), 0, st, x, g, b, y, rows)); break;
+        case 256: B2D_CUDA(launch_k(layernorm_rows_kernel<256>, dim3(blocks), dim3(256), 0, st, x, g, b, y, rows)); break;
+        case 512: B2D_CUDA(launch_k(layernorm_rows_kernel<512>, dim3(blocks), dim3(256), 0, st, x, g, b, y, rows)); break;
         default: return fail(-1, "layernorm: unsupported channel count " + std::to_string(C));
     }
     B2D_CUDA(cudaGetLastError());
@@ -79,6 +81,8 @@ __host__ __device__ constexpr int fa_smem_bytes() {
 template <int D>
 __global__ void __launch_bounds__(128) flash_attn_kernel(const f16* __restrict__ qkv, f16* __restrict__ o, int L, int C,
                                                          float scale_log2e) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int LDS = D + 8;  // padded row (elements): conflict-free 32-bit fragment loads and ldmatrix
     extern __shared__ __align__(16) uint8_t fa_smem[];
     f16* sK = reinterpret_cast<f16*>(fa_smem);          // [2][FA_BK][LDS]
@@ -107,13 +111,21 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const f16* __restrict__
         }
     }
 
-    float oacc[D / 8][4];
+    // O accumulators; n-tile D/8 is the "ones" column of V (pad block of the smem rows): its column 0 accumulates the
+    // softmax denominator in fp32 on the tensor pipe, with the same online rescaling as O.
+    float oacc[D / 8 + 1][4];
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int i = 0; i <= D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY;
 
     const int ntiles = (L + FA_BK - 1) / FA_BK;
     constexpr int CPR = D / 8;  // 16-byte chunks per row
+
+    // pad block of every V row (never touched by cp.async): [1, 0, 0, 0, 0, 0, 0, 0]
+    for (int i = threadIdx.x; i < 2 * FA_BK; i += 128) {
+        uint4 one = make_uint4(0x00003C00u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(sV + (size_t)i * LDS + D) = one;
+    }
 
     auto load_tile = [&](int tile, int buf) {
         const int k0 = tile * FA_BK;
@@ -179,34 +191,26 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const f16* __restrict__
         m0 = mx0;
         m1 = mx1;
         const float ms0 = mx0 * scale_log2e, ms1 = mx1 * scale_log2e;
-        float rs0 = 0.f, rs1 = 0.f;
+        // P = 2^(s*scale - m*scale) straight into the fp16x2 A fragments (2 exponentials per SFU op)
         uint32_t pf[FA_BK / 16][4];
 #pragma unroll
         for (int j = 0; j < FA_BK / 8; ++j) {
-            const float p0 = ex2_approx(fmaf(s[j][0], scale_log2e, -ms0));
-            const float p1 = ex2_approx(fmaf(s[j][1], scale_log2e, -ms0));
-            const float p2 = ex2_approx(fmaf(s[j][2], scale_log2e, -ms1));
-            const float p3 = ex2_approx(fmaf(s[j][3], scale_log2e, -ms1));
-            rs0 += p0 + p1;
-            rs1 += p2 + p3;
-            pf[j >> 1][(j & 1) * 2 + 0] = pack_h2(p0, p1);
-            pf[j >> 1][(j & 1) * 2 + 1] = pack_h2(p2, p3);
+            pf[j >> 1][(j & 1) * 2 + 0] = ex2_h2(fmaf(s[j][0], scale_log2e, -ms0), fmaf(s[j][1], scale_log2e, -ms0));
+            pf[j >> 1][(j & 1) * 2 + 1] = ex2_h2(fmaf(s[j][2], scale_log2e, -ms1), fmaf(s[j][3], scale_log2e, -ms1));
         }
-        l0 = l0 * corr0 + rs0;
-        l1 = l1 * corr1 + rs1;
 #pragma unroll
-        for (int i = 0; i < D / 8; ++i) {
+        for (int i = 0; i <= D / 8; ++i) {
             oacc[i][0] *= corr0;
             oacc[i][1] *= corr0;
             oacc[i][2] *= corr1;
             oacc[i][3] *= corr1;
         }
-        // ---- O += P V : A = P (from registers), B[k][n] = V[key k][dim n] via ldmatrix.trans
+        // ---- O += P V : A = P (from registers), B[k][n] = V[key k][dim n] via ldmatrix.trans (+ the ones column)
 #pragma unroll
         for (int kk = 0; kk < FA_BK / 16; ++kk) {
             const uint32_t vrow = smem_u32(tV + (kk * 16 + (lane & 15)) * LDS);
 #pragma unroll
-            for (int i = 0; i < D / 8; ++i) {
+            for (int i = 0; i <= D / 8; ++i) {
                 uint32_t b0, b1;
                 ldmatrix_x2_trans(b0, b1, vrow + i * 16);
                 mma_f16_16816(oacc[i], pf[kk], b0, b1);
@@ -216,11 +220,9 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const f16* __restrict__
     }
     cp_async_wait<0>();
 
-    // ---- finalise: row sums across the quad, normalise, store
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // ---- finalise: the denominator sits in column 0 of the ones tile (lane t == 0 of each quad)
+    const float l0 = __shfl_sync(0xffffffffu, oacc[D / 8][0], lane & ~3);
+    const float l1 = __shfl_sync(0xffffffffu, oacc[D / 8][2], lane & ~3);
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     const int r0 = q0 + g, r1 = q0 + g + 8;
     f16* ob = o + (size_t)b * L * C + (size_t)head * D + 2 * t;
@@ -238,6 +240,8 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const f16* __restrict__
 template <int D>
 __global__ void __launch_bounds__(128) attn_small_d_kernel(const f16* __restrict__ qkv, f16* __restrict__ o, int L, int C,
                                                            float scale_log2e) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sK[128][D];
     __shared__ float sV[128][D];
     const int head = blockIdx.y, b = blockIdx.z;
@@ -310,13 +314,13 @@ inline int flash_attn_launch(const f16* qkv, f16* o, int B, int L, int C, int he
     const float scale_log2e = 1.4426950408889634f / sqrtf((float)D);
     dim3 grid((L + FA_BQ - 1) / FA_BQ, heads, B);
     switch (D) {
-        case 2: attn_small_d_kernel<2><<<dim3((L + 127) / 128, heads, B), 128, 0, st>>>(qkv, o, L, C, scale_log2e); break;
-        case 4: attn_small_d_kernel<4><<<dim3((L + 127) / 128, heads, B), 128, 0, st>>>(qkv, o, L, C, scale_log2e); break;
-        case 8: attn_small_d_kernel<8><<<dim3((L + 127) / 128, heads, B), 128, 0, st>>>(qkv, o, L, C, scale_log2e); break;
-        case 16: flash_attn_kernel<16><<<grid, 128, fa_smem_bytes<16>(), st>>>(qkv, o, L, C, scale_log2e); break;
-        case 32: flash_attn_kernel<32><<<grid, 128, fa_smem_bytes<32>(), st>>>(qkv, o, L, C, scale_log2e); break;
-        case 64: flash_attn_kernel<64><<<grid, 128, fa_smem_bytes<64>(), st>>>(qkv, o, L, C, scale_log2e); break;
-        case 128: flash_attn_kernel<128><<<grid, 128, fa_smem_bytes<128>(), st>>>(qkv, o, L, C, scale_log2e); break;
+        case 2: B2D_CUDA(launch_k(attn_small_d_kernel<2>, dim3(dim3((L + 127) / 128, heads, B)), dim3(128), 0, st, qkv, o, L, C, scale_log2e)); break;
+        case 4: B2D_CUDA(launch_k(attn_small_d_kernel<4>, dim3(dim3((L + 127) / 128, heads, B)), dim3(128), 0, st, qkv, o, L, C, scale_log2e)); break;
+        case 8: B2D_CUDA(launch_k(attn_small_d_kernel<8>, dim3(dim3((L + 127) / 128, heads, B)), dim3(128), 0, st, qkv, o, L, C, scale_log2e)); break;
+        case 16: B2D_CUDA(launch_k(flash_attn_kernel<16>, dim3(grid), dim3(128), fa_smem_bytes<16>(), st, qkv, o, L, C, scale_log2e)); break;
+        case 32: B2D_CUDA(launch_k(flash_attn_kernel<32>, dim3(grid), dim3(128), fa_smem_bytes<32>(), st, qkv, o, L, C, scale_log2e)); break;
+        case 64: B2D_CUDA(launch_k(flash_attn_kernel<64>, dim3(grid), dim3(128), fa_smem_bytes<64>(), st, qkv, o, L, C, scale_log2e)); break;
+        case 128: B2D_CUDA(launch_k(flash_attn_kernel<128>, dim3(grid), dim3(128), fa_smem_bytes<128>(), st, qkv, o, L, C, scale_log2e)); break;
         default: return fail(-1, "attention: unsupported head_dim " + std::to_string(D));
     }
     B2D_CUDA(cudaGetLastError());

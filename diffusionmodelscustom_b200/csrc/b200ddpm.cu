@@ -16,6 +16,7 @@
 
 namespace b2d {
 thread_local Status g_status;
+int g_pdl_enabled = getenv("B2D_NO_PDL") ? 0 : 1;
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -244,7 +245,12 @@ static int pack_family_r(Handle* h) {
         const int cin_total = h->cfg.c_hr + h->cfg.has_lsm + h->cfg.has_topo + h->cfg.cond_channels;
         if (w->shape[0] != 64 || w->shape[1] != cin_total || w->shape[2] != 8 || w->shape[3] != 8)
             return fail(-3, "encoder.conv1.weight shape does not match the configured input channels");
-        B2D_TRY(upload_f32(h, "stem.w", w->v));
+        // transpose to [Cin_total][64 taps][64 couts] so the stem kernel stages one channel's weights with 16-byte loads
+        std::vector<float> wt((size_t)cin_total * 64 * 64);
+        for (int co = 0; co < 64; ++co)
+            for (int ci = 0; ci < cin_total; ++ci)
+                for (int tap = 0; tap < 64; ++tap) wt[((size_t)ci * 64 + tap) * 64 + co] = w->v[((size_t)co * cin_total + ci) * 64 + tap];
+        B2D_TRY(upload_f32(h, "stem.w", wt));
     }
     B2D_TRY(pack_conv(h, "conv2", E + "conv2.weight", "", E + "bn1"));
     for (int li = 1; li <= 4; ++li)
@@ -360,6 +366,9 @@ struct Builder {
             ops.push_back([pl](cudaStream_t st) { return conv_launch_simt(pl->p, st); });
         } else {
             if (conv_plan_build(*pl, h->num_sms) != 0) { err = -1; return; }
+            if (pl->ws_floats) {
+                if (h->alloc(&pl->p.ws, pl->ws_floats) != 0) { err = -2; return; }
+            }
             ops.push_back([pl](cudaStream_t st) { return conv_launch_tc(*pl, st); });
         }
     }
@@ -413,7 +422,7 @@ struct Builder {
         ops.meta("in_stats", "plane_stats", 0, 2.0 * B * HW * C);
         ops.push_back([=](cudaStream_t s) {
             dim3 grid(nslab, ngrp, Bc);
-            plane_stats_kernel<<<grid, 256, 0, s>>>(x, partial, counters, st, HW, C, ppc);
+            B2D_CUDA(launch_k(plane_stats_kernel, dim3(grid), dim3(256), 0, s, x, partial, counters, st, HW, C, ppc));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -425,7 +434,7 @@ struct Builder {
         ops.meta("in_apply", "instnorm_apply", 0, 2.0 * B * HW * C * (skip ? 3 : 2));
         ops.push_back([=](cudaStream_t s) {
             int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
-            instnorm_apply_kernel<<<blocks, 256, 0, s>>>(x, st, skip, vec, vec_stride, y, HW, C, total8);
+            B2D_CUDA(launch_k(instnorm_apply_kernel, dim3(blocks), dim3(256), 0, s, x, st, skip, vec, vec_stride, y, HW, C, total8));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -468,8 +477,9 @@ static int build_program_r(Handle* h, int B) {
         const float* tb = bd.W<float>("temb.b");
         ops.meta("temb", "temb_project", 2.0 * B * TS * 256, 4.0 * TS * 256);
         ops.push_back([=](cudaStream_t st) {
-            temb_project_kernel<<<B, 256, 0, st>>>(hh->d_t, hh->has_y ? hh->d_y : nullptr, label, ei, dd, tw, tb, temb, 1024,
-                                                   TS);
+            dim3 grid((TS + TEMB_OC - 1) / TEMB_OC, (B + TEMB_SB - 1) / TEMB_SB);
+            B2D_CUDA(launch_k(temb_project_kernel, dim3(grid), dim3(256), 0, st, hh->d_t, hh->has_y ? hh->d_y : nullptr, label, ei, dd, tw, tb, temb, 1024,
+                                                      TS, B));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -484,11 +494,11 @@ static int build_program_r(Handle* h, int B) {
         ops.meta("conv1", "stem_conv", 2.0 * B * ho * ho * 64 * 64 * chr,
                  (double)B * (4.0 * chr * Hh * Hh + ho * ho * 64 * (2 + 4)));
         ops.push_back([=](cudaStream_t st) {
-            dim3 grid(ho / 8, ho / 8, B);
+            dim3 grid(ho / 16, ho / 16, B);
             const bool have_cond = (cin_total > chr);
-            stem_conv_kernel<8, 2><<<grid, 256, 0, st>>>(hh->cur_x, chr, Hh, Hh, sw, cin_total, 0,
+            B2D_CUDA(launch_k(stem_conv_kernel<8, 2>, dim3(grid), dim3(256), 0, st, hh->cur_x, chr, Hh, Hh, sw, cin_total, 0,
                                                          have_cond ? hh->d_cond_pre : nullptr, temb + TEMB_ENC_OFF[0], TS,
-                                                         f1_pre, nullptr, ho, ho, 3);
+                                                         f1_pre, nullptr, ho, ho, 3));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -566,7 +576,7 @@ static int build_program_r(Handle* h, int B) {
         ops.meta("final.conv", "tail_conv", 2.0 * B * Hh * Hh * 576 * cout, (double)B * Hh * Hh * (64 * 2 + 4 * cout));
         ops.push_back([=](cudaStream_t s2) {
             dim3 grid((Hh + 31) / 32, (Hh + 7) / 8, B);
-            tail_conv_kernel<<<grid, 256, 0, s2>>>(up, st, tw, tb, hh->cur_eps, Hh, Hh, cout);
+            B2D_CUDA(launch_k(tail_conv_kernel, dim3(grid), dim3(256), TAIL_SMEM, s2, up, st, tw, tb, hh->cur_eps, Hh, Hh, cout));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -745,10 +755,10 @@ int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, con
     if (c.has_topo) B2D_TRY(put(topo, 1));
     if (c.cond_channels) B2D_TRY(put(cond, c.cond_channels));
     const int cin_total = c.c_hr + ccond;
-    dim3 grid(H / 2 / 8, H / 2 / 8, B);
-    stem_conv_kernel<8, 2><<<grid, 256, 0, st>>>(h->d_cond_stack, ccond, H, H, reinterpret_cast<float*>(h->dev["stem.w"]),
+    dim3 grid(H / 2 / 16, H / 2 / 16, B);
+    B2D_CUDA(launch_k(stem_conv_kernel<8, 2>, dim3(grid), dim3(256), 0, st, h->d_cond_stack, ccond, H, H, reinterpret_cast<float*>(h->dev["stem.w"]),
                                                  cin_total, c.c_hr, nullptr, nullptr, 0, nullptr, h->d_cond_pre, H / 2, H / 2,
-                                                 3);
+                                                 3));
     B2D_CUDA(cudaGetLastError());
     return 0;
 }
@@ -790,15 +800,16 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
         h->cur_x = x_inout;
         h->cur_eps = h->d_eps;
         B2D_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        int rc = run_step_ops(h, cs);
-        if (rc == 0) {
+        auto tail_ops = [&]() -> int {
             const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)h->num_sms * 8);
-            posterior_update_kernel<<<blocks, 256, 0, cs>>>(x_inout, h->d_eps, noise, h->d_alphas, h->d_betas, h->d_alpha_hat,
-                                                            h->d_step, h->d_t, B, n, per_sample, seed, sample_offset,
-                                                            noise_scale);
-            step_advance_kernel<<<1, 256, 0, cs>>>(h->d_step, h->d_t, B);
-            if (cudaGetLastError() != cudaSuccess) rc = fail(-2, "launch failed during graph capture");
-        }
+            B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, cs, x_inout, h->d_eps, noise, h->d_alphas,
+                              h->d_betas, h->d_alpha_hat, h->d_step, h->d_t, B, n, per_sample, seed, sample_offset,
+                              noise_scale));
+            B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, cs, h->d_step, h->d_t, B));
+            return 0;
+        };
+        int rc = run_step_ops(h, cs);
+        if (rc == 0) rc = tail_ops();
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
         if (rc) return rc;
@@ -812,8 +823,8 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
         h->graph_key = key;
     }
     const int T = h->T;
-    fill_int_kernel<<<(B + 255) / 256, 256, 0, st>>>(h->d_t, T - 1, B);
-    fill_int_kernel<<<1, 32, 0, st>>>(h->d_step, T - 1, 1);
+    B2D_CUDA(launch_k(fill_int_kernel, dim3((B + 255) / 256), dim3(256), 0, st, h->d_t, T - 1, B));
+    B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, h->d_step, T - 1, 1));
     B2D_CUDA(cudaGetLastError());
     for (int i = T - 1; i >= 1; --i) B2D_CUDA(cudaGraphLaunch(h->graph_exec, st));
     h->last_launches = (int64_t)h->graph_nodes * (T - 1) + 2;
@@ -965,7 +976,17 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     B2D_TRY(conv_tc_init_attrs());
     B2D_TRY(conv_plan_build(pl, sms));
-    return conv_launch_tc(pl, as_stream(stream));
+    float* ws = nullptr;
+    if (pl.ws_floats) {
+        B2D_CUDA(cudaMalloc(&ws, pl.ws_floats * sizeof(float)));
+        pl.p.ws = ws;
+    }
+    int rc = conv_launch_tc(pl, as_stream(stream));
+    if (ws) {
+        cudaStreamSynchronize(as_stream(stream));
+        cudaFree(ws);
+    }
+    return rc;
 }
 
 int b2d_op_layernorm(const void* x, const float* gamma, const float* beta, void* y, int32_t rows, int32_t C, void* stream) {
@@ -991,11 +1012,11 @@ int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t v
     unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n_stats + n_part);
     cudaMemsetAsync(counters, 0, n_cnt * 4, st);
     dim3 grid(nslab, ngrp, B);
-    plane_stats_kernel<<<grid, 256, 0, st>>>((const f16*)x, partial, counters, stats, HW, C, 256);
+    B2D_CUDA(launch_k(plane_stats_kernel, dim3(grid), dim3(256), 0, st, (const f16*)x, partial, counters, stats, HW, C, 256));
     const size_t total8 = (size_t)B * HW * C / 8;
     const int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
-    instnorm_apply_kernel<<<blocks, 256, 0, st>>>((const f16*)x, stats, (const f16*)skip, vec, vec_stride, (f16*)y, HW, C,
-                                                  total8);
+    B2D_CUDA(launch_k(instnorm_apply_kernel, dim3(blocks), dim3(256), 0, st, (const f16*)x, stats, (const f16*)skip, vec, vec_stride, (f16*)y, HW, C,
+                                                  total8));
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(st);
     cudaFree(ws);
@@ -1009,13 +1030,13 @@ int b2d_op_posterior_update(float* x, const float* eps, const float* z, const fl
     cudaStream_t st = as_stream(stream);
     int* d_step = nullptr;
     B2D_CUDA(cudaMalloc(&d_step, 16));
-    fill_int_kernel<<<1, 32, 0, st>>>(d_step, i, 1);
+    B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, d_step, i, 1));
     const size_t n = (size_t)B * per_sample;
     const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)148 * 8);
     // z (if given) is the noise of THIS step: bias the pointer so that noise + i*n lands on it
     const float* noise = z ? z - (size_t)i * n : nullptr;
-    posterior_update_kernel<<<blocks, 256, 0, st>>>(x, eps, noise, alphas, betas, alpha_hat, d_step, nullptr, B, n,
-                                                    (size_t)per_sample, seed, sample_offset, noise_scale);
+    B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, x, eps, noise, alphas, betas, alpha_hat, d_step, nullptr, B, n,
+                                                    (size_t)per_sample, seed, sample_offset, noise_scale));
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(st);
     cudaFree(d_step);

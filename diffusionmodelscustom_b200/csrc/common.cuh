@@ -46,6 +46,31 @@ inline int fail(int code, const std::string& m) {
         if (_r != 0) return _r; \
     } while (0)
 
+// ---------------------------------------------------------------- launches with programmatic dependent launch (PDL)
+// Every kernel of the step calls pdl_launch_dependents() first (the next kernel's CTAs may be scheduled and run their
+// prologue as soon as SM resources free up) and pdl_wait() before touching any global memory (returns once the
+// preceding kernel in the stream/graph has completed and its writes are visible).  Since each kernel only completes
+// after its own wait, completion — and therefore every RAW/WAR dependency — stays transitively ordered.
+extern int g_pdl_enabled;  // B2D_NO_PDL=1 in the environment disables the launch attribute (A/B measurement)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl_enabled;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -205,6 +230,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// two exponentials per SFU operation: packs (a, b) to fp16x2 and returns 2^a, 2^b as fp16x2 (the P fragment of P.V)
+__device__ __forceinline__ uint32_t ex2_h2(float a, float b) {
+    uint32_t h, r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));   // low half <- a, high half <- b
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+    return r;
 }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

@@ -35,6 +35,9 @@ struct ConvParams {
     int post_stride;
     int act;  // 0 none, 1 relu, 2 gelu(erf)
     f16* out;
+    // split-K: gridDim.z = splits CTAs of one cluster share an output tile; fp32 partials go through `ws`
+    int splits;
+    float* ws;  // [tiles][splits][128][BN] fp32
     // simt only
     const f16* in;
     const f16* w;
@@ -45,6 +48,42 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     if (act == 2) return gelu_erf(v);
     return v;
 }
+
+// Epilogue of 8 consecutive channels of one output pixel: bias -> +residual -> act -> +post_add -> fp16 store (16 B).
+__device__ __forceinline__ void conv_epilogue8(const ConvParams& p, float (&f)[8], int n, size_t off, int c0) {
+    if (p.bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    if (p.residual) {
+        const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(p.residual + off));
+        float2 t;
+        t = unpack_h2(r4.x); f[0] += t.x; f[1] += t.y;
+        t = unpack_h2(r4.y); f[2] += t.x; f[3] += t.y;
+        t = unpack_h2(r4.z); f[4] += t.x; f[5] += t.y;
+        t = unpack_h2(r4.w); f[6] += t.x; f[7] += t.y;
+    }
+    if (p.act) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = apply_act(f[j], p.act);
+    }
+    if (p.post_add) {
+        const float* pa = p.post_add + (size_t)n * p.post_stride + c0;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(pa));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(pa + 4));
+        f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+        f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    }
+    uint4 o;
+    o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
+    o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p.out + off) = o;
+}
+
+__device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------ tcgen05 path
 constexpr int CONV_TC_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
@@ -62,6 +101,7 @@ __host__ __device__ constexpr int conv_smem_bytes() {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(CONV_TC_THREADS)
     conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                              // STAGES x 16 KB
@@ -104,18 +144,24 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();   // everything above overlapped the previous kernel's tail; global memory is touched only below
 
     const int cblocks = p.Cin >> 6;
-    const int num_kb = p.R * p.S * cblocks;
+    const int total_kb = p.R * p.S * cblocks;
+    const int split = blockIdx.z;                              // == rank in the (1,1,splits) cluster
+    const int kb_begin = (int)(((long long)total_kb * split) / p.splits);
+    const int kb_end = (int)(((long long)total_kb * (split + 1)) / p.splits);
+    const int num_kb = kb_end - kb_begin;
 
     if (warp == 0) {
         // ===================== TMA producer (one lane) =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tap = 0; tap < p.R * p.S; ++tap) {
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                const int tap = kb / cblocks, cb = kb - tap * cblocks;
                 const int r = tap / p.S, s = tap - r * p.S;
-                for (int cb = 0; cb < cblocks; ++cb) {
+                {
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], conv_stage_bytes<BN>());
                     void* a_dst = sA + stage * CONV_A_BYTES;
@@ -136,6 +182,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (one lane) =====================
         if (lane == 0) {
@@ -185,6 +232,22 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
 
         mbar_wait(accum_full, 0);
         tc_fence_after();
+        if (p.splits > 1) {
+            // raw fp32 partial tile -> workspace (this thread's row: BN contiguous floats)
+            const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            float* wrow = p.ws + ((tile_id * p.splits + split) * 128 + row) * BN;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    __stcg(reinterpret_cast<float4*>(wrow + ch * 32 + j),
+                           make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3])));
+            }
+        } else
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
             uint32_t v[32];
@@ -239,6 +302,46 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
             }
         }
     }
+    if (p.splits > 1) {
+        // all CTAs of the cluster have written their partial tiles; each finalises 128/splits rows in fixed split order
+        __threadfence();
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        if (warp >= 2) {
+            const int et = threadIdx.x - 64;                       // 0..127
+            const int rows_per = 128 / p.splits;
+            const int items = rows_per * (BN / 8);
+            const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            const float* wtile = p.ws + tile_id * p.splits * 128 * BN;
+            for (int it = et; it < items; it += 128) {
+                const int row = split * rows_per + it / (BN / 8);
+                const int c8 = (it % (BN / 8)) * 8;
+                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int sp = 0; sp < p.splits; ++sp) {
+                    const float4* src = reinterpret_cast<const float4*>(wtile + ((size_t)sp * 128 + row) * BN + c8);
+                    const float4 a = __ldcg(src), b = __ldcg(src + 1);
+                    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
+                    f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+                }
+                const int lw = row % p.TW;
+                const int lh = (row / p.TW) % p.TH;
+                const int ln = row / (p.TW * p.TH);
+                const int n = n0 + ln, h = h0 + lh, w = w0 + lw;
+                if (n >= p.B) continue;
+                int cbase;
+                size_t pix;
+                if (p.convt) {
+                    const int ab = (nblk * BN) / p.CoutT;
+                    cbase = (nblk * BN) - ab * p.CoutT;
+                    pix = ((size_t)n * (2 * p.Ho) + (2 * h + (ab >> 1))) * (size_t)(2 * p.Wo) + (2 * w + (ab & 1));
+                } else {
+                    cbase = nblk * BN;
+                    pix = ((size_t)n * p.Ho + h) * (size_t)p.Wo + w;
+                }
+                conv_epilogue8(p, f, n, pix * (size_t)p.CoutT + cbase + c8, cbase + c8);
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -249,6 +352,8 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
 
 // ------------------------------------------------------------------------------------------------ SIMT cross-check
 __global__ void conv_simt_kernel(const ConvParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t total = (size_t)p.B * p.Ho * p.Wo * p.Cout;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int co = (int)(idx % p.Cout);
@@ -337,8 +442,10 @@ struct ConvPlan {
     ConvParams p;
     CUtensorMap tmA, tmB;
     int bn = 0;
+    int stages = 4;
     dim3 grid;
     bool tc_ready = false;
+    size_t ws_floats = 0;  // split-K workspace the caller must provide in p.ws before launching
 };
 
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -361,7 +468,17 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     int bn = 64;
     if (p.Cout % 128 == 0 && (!p.convt || p.CoutT % 128 == 0) && mtiles * (p.Cout / 128) >= num_sms) bn = 128;
     pl.bn = bn;
-    pl.grid = dim3(mtiles, p.Cout / bn, 1);
+    // split-K over a (1,1,S) cluster when the tile grid cannot fill the machine and K is deep
+    const int tiles = mtiles * (p.Cout / bn);
+    const int total_kb = p.R * p.S * (p.Cin / 64);
+    int splits = 1;
+    while (splits < 8 && tiles * splits * 2 <= num_sms && total_kb / (splits * 2) >= 4) splits *= 2;
+    p.splits = splits;
+    pl.ws_floats = splits > 1 ? (size_t)tiles * splits * 128 * bn : 0;
+    // deep pipelines for deep-K problems that leave SMs to spare anyway (the TMA round trip paces them)
+    pl.stages = (bn == 64) ? ((total_kb / splits >= 12 && tiles * splits <= num_sms) ? 8 : 4)
+                           : ((total_kb / splits >= 12 && tiles * splits <= num_sms) ? 6 : 3);
+    pl.grid = dim3(mtiles, p.Cout / bn, splits);
     const uint64_t C = p.Cin, W = p.Wi, H = p.Hi, B = p.B;
     if (p.stride == 1) {
         uint64_t dims[4] = {C, W, H, B};
@@ -383,34 +500,52 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     return 0;
 }
 
-constexpr int CONV_STAGES_64 = 4;
-constexpr int CONV_STAGES_128 = 3;
-
+template <int BN, int STAGES>
+inline int conv_tc_set_attr() {
+    B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_smem_bytes<BN, STAGES>()));
+    return 0;
+}
 inline int conv_tc_init_attrs() {
-    B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64, CONV_STAGES_64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_smem_bytes<64, CONV_STAGES_64>()));
-    B2D_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128, CONV_STAGES_128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_smem_bytes<128, CONV_STAGES_128>()));
+    B2D_TRY((conv_tc_set_attr<64, 4>()));
+    B2D_TRY((conv_tc_set_attr<64, 8>()));
+    B2D_TRY((conv_tc_set_attr<128, 3>()));
+    B2D_TRY((conv_tc_set_attr<128, 6>()));
+    return 0;
+}
+
+template <int BN, int STAGES>
+inline int conv_tc_launch_t(const ConvPlan& pl, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = pl.grid;
+    cfg.blockDim = dim3(CONV_TC_THREADS);
+    cfg.dynamicSmemBytes = conv_smem_bytes<BN, STAGES>();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = pl.p.splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl_enabled;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    B2D_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, pl.tmA, pl.tmB, pl.p));
     return 0;
 }
 
 inline int conv_launch_tc(const ConvPlan& pl, cudaStream_t st) {
     B2D_CHECK(pl.tc_ready, "conv plan not built");
-    if (pl.bn == 64)
-        conv_tc_kernel<64, CONV_STAGES_64>
-            <<<pl.grid, CONV_TC_THREADS, conv_smem_bytes<64, CONV_STAGES_64>(), st>>>(pl.tmA, pl.tmB, pl.p);
-    else
-        conv_tc_kernel<128, CONV_STAGES_128>
-            <<<pl.grid, CONV_TC_THREADS, conv_smem_bytes<128, CONV_STAGES_128>(), st>>>(pl.tmA, pl.tmB, pl.p);
-    B2D_CUDA(cudaGetLastError());
-    return 0;
+    B2D_CHECK(pl.p.splits == 1 || pl.p.ws != nullptr, "split-K plan without workspace");
+    if (pl.bn == 64) return pl.stages == 8 ? conv_tc_launch_t<64, 8>(pl, st) : conv_tc_launch_t<64, 4>(pl, st);
+    return pl.stages == 6 ? conv_tc_launch_t<128, 6>(pl, st) : conv_tc_launch_t<128, 3>(pl, st);
 }
 
 inline int conv_launch_simt(const ConvParams& p, cudaStream_t st) {
     const size_t total = (size_t)p.B * p.Ho * p.Wo * p.Cout;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    conv_simt_kernel<<<blocks, 256, 0, st>>>(p);
+    B2D_CUDA(launch_k(conv_simt_kernel, dim3(blocks), dim3(256), 0, st, p));
     B2D_CUDA(cudaGetLastError());
     return 0;
 }

@@ -12,6 +12,9 @@ namespace b2d {
 //   out[b][o] = bias[o] + sum_k W[o][k] * silu(emb_sel(o)[k]),  rows o < n_enc use e, the rest use d.
 // Family D (unet_ms.py:138-146) uses the [sin|cos] layout with base 10000 for every projection (n_enc = n_out, inv table differs).
 constexpr int TEMB_DIM = 256;
+constexpr int TEMB_SB = 8;    // samples per CTA (weights are read once per 8 samples)
+constexpr int TEMB_OC = 64;   // outputs per CTA
+// grid = (ceil(n_out/64), ceil(B/8)), 256 threads.
 __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict__ t, const int* __restrict__ y,
                                                            const float* __restrict__ label_emb,  // [ncls][256] or null
                                                            const float* __restrict__ enc_inv,    // [128]
@@ -19,31 +22,58 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
                                                            const float* __restrict__ W,          // [n_out][256]
                                                            const float* __restrict__ bias,       // [n_out]
                                                            float* __restrict__ out,              // [B][n_out]
-                                                           int n_enc, int n_out) {
-    __shared__ float se[TEMB_DIM], sd[TEMB_DIM];
-    const int b = blockIdx.x;
-    const float tf = (float)t[b];
+                                                           int n_enc, int n_out, int B) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float se[TEMB_SB][TEMB_DIM], sd[TEMB_SB][TEMB_DIM];
+    const int b0 = blockIdx.y * TEMB_SB;
+    const int o0 = blockIdx.x * TEMB_OC;
+    const bool need_enc = o0 < n_enc, need_dec = o0 + TEMB_OC > n_enc;
     {
         const int k = threadIdx.x;  // 256 threads <-> 256 embedding entries
         const int j = k & 127;
-        const float a = tf * enc_inv[j];
-        float e = (k < 128) ? sinf(a) : cosf(a);
-        if (label_emb != nullptr && y != nullptr) e += label_emb[(size_t)y[b] * TEMB_DIM + k];
-        se[k] = silu(e);
-        const float a2 = __fdiv_rn(tf, dec_div[k >> 1]);
-        const float d = (k & 1) ? cosf(a2) : sinf(a2);
-        sd[k] = silu(d);
+        const float inv = enc_inv[j], div = dec_div[k >> 1];
+#pragma unroll
+        for (int sidx = 0; sidx < TEMB_SB; ++sidx) {
+            const int b = min(b0 + sidx, B - 1);
+            const float tf = (float)t[b];
+            if (need_enc) {
+                const float a = tf * inv;
+                float e = (k < 128) ? sinf(a) : cosf(a);
+                if (label_emb != nullptr && y != nullptr) e += label_emb[(size_t)y[b] * TEMB_DIM + k];
+                se[sidx][k] = silu(e);
+            }
+            if (need_dec) {
+                const float a2 = __fdiv_rn(tf, div);
+                sd[sidx][k] = silu((k & 1) ? cosf(a2) : sinf(a2));
+            }
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int o = warp; o < n_out; o += 8) {
+#pragma unroll 1
+    for (int oi = 0; oi < TEMB_OC / 8; ++oi) {
+        const int o = o0 + warp * (TEMB_OC / 8) + oi;
+        if (o >= n_out) break;
         const float* w = W + (size_t)o * TEMB_DIM;
-        const float* e = (o < n_enc) ? se : sd;
-        float acc = 0.f;
+        const float(*e)[TEMB_DIM] = (o < n_enc) ? se : sd;
+        float wv[8];
 #pragma unroll
-        for (int k = lane; k < TEMB_DIM; k += 32) acc = fmaf(w[k], e[k], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) out[(size_t)b * n_out + o] = acc + bias[o];
+        for (int q = 0; q < 8; ++q) wv[q] = __ldg(w + lane + 32 * q);
+        float acc[TEMB_SB];
+#pragma unroll
+        for (int sidx = 0; sidx < TEMB_SB; ++sidx) {
+            float a = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a = fmaf(wv[q], e[sidx][lane + 32 * q], a);
+            acc[sidx] = warp_sum(a);
+        }
+        if (lane < TEMB_SB && b0 + lane < B) {
+            float v = acc[0];
+#pragma unroll
+            for (int sidx = 1; sidx < TEMB_SB; ++sidx) v = (lane == sidx) ? acc[sidx] : v;
+            out[(size_t)(b0 + lane) * n_out + o] = v + bias[o];
+        }
     }
 }
 
@@ -54,27 +84,35 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
 //   out[b,ho,wo,co] = sum_{c,r,s} in[b,c,ho*st+r-pad,wo*st+s-pad] * w[co][c][r][s] (+ add[b,ho,wo,co]) (+ vec[b][co])
 // Encoder.conv1 (modules_DANRA_conditional.py:178-183, :260) is linear in its input channels, so the conditioning
 // channels' contribution is computed once per sampling job (out_f32) and added each step through `add`.
-// CTA: 8x8 output pixels x 64 channels, 256 threads (thread = pixel p, channel group cg of 16).
+// CTA: 16x16 output pixels x 64 channels, 256 threads; thread = 4 consecutive output pixels of one row x 16 channels
+// (64 fp32 accumulators): per filter row the thread loads its 4*STRIDE+KS-STRIDE inputs once and reuses them over the
+// KS taps and 4 pixels, so shared-memory traffic is ~1 load per 11 FMAs.
 template <int KS, int STRIDE>
 __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ in, int Cx, int Hi, int Wi,
-                                                        const float* __restrict__ w,  // [64][Cx][KS][KS]
-                                                        int w_cstride_total,          // channels in the full weight (Cin_total)
+                                                        const float* __restrict__ w,  // packed [Cin_total][KS*KS][64]
+                                                        int w_cstride_total,          // channels in the full weight (unused)
                                                         int w_coffset,                // first weight channel used
                                                         const float* __restrict__ add,  // [B,Ho,Wo,64] fp32 or null
                                                         const float* __restrict__ vec, int vec_stride,  // [B][..] or null
                                                         f16* __restrict__ out_f16, float* __restrict__ out_f32, int Ho,
                                                         int Wo, int pad) {
-    constexpr int PT = 8;                         // output tile side
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int PT = 16;                        // output tile side
     constexpr int IT = (PT - 1) * STRIDE + KS;    // input tile side
+    constexpr int NX = 3 * STRIDE + KS;           // inputs one thread needs per filter row (4 pixels)
     __shared__ float s_in[IT][IT + 1];
     __shared__ __align__(16) float s_w[KS * KS][64];
     const int b = blockIdx.z;
     const int ho0 = blockIdx.y * PT, wo0 = blockIdx.x * PT;
-    const int p = threadIdx.x & 63, cg = threadIdx.x >> 6;
-    const int py = p >> 3, px = p & 7;
-    float acc[16];
+    const int cg = threadIdx.x >> 6;              // warp-uniform channel group (16 channels)
+    const int pg = threadIdx.x & 63;              // pixel group: row py, columns 4*px4 .. 4*px4+3
+    const int py = pg >> 2, px4 = pg & 3;
+    float acc[4][16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[j][i] = 0.f;
     for (int c = 0; c < Cx; ++c) {
         __syncthreads();
         const float* ip = in + ((size_t)b * Cx + c) * Hi * Wi;
@@ -83,51 +121,71 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
             const int gy = ho0 * STRIDE - pad + iy, gx = wo0 * STRIDE - pad + ix;
             s_in[iy][ix] = (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) ? ip[(size_t)gy * Wi + gx] : 0.f;
         }
-        for (int i = threadIdx.x; i < KS * KS * 64; i += 256) {
-            const int co = i & 63, tap = i >> 6;
-            s_w[tap][co] = w[((size_t)co * w_cstride_total + (w_coffset + c)) * (KS * KS) + tap];
+        {
+            const float4* wsrc = reinterpret_cast<const float4*>(w + (size_t)(w_coffset + c) * (KS * KS * 64));
+            float4* wdst = reinterpret_cast<float4*>(&s_w[0][0]);
+            for (int i = threadIdx.x; i < KS * KS * 16; i += 256) wdst[i] = __ldg(wsrc + i);
         }
         __syncthreads();
-#pragma unroll 4
+#pragma unroll 1
         for (int r = 0; r < KS; ++r) {
+            float xin[NX];
+            const float* row = &s_in[py * STRIDE + r][px4 * 4 * STRIDE];
 #pragma unroll
-            for (int s = 0; s < KS; ++s) {
-                const float v = s_in[py * STRIDE + r][px * STRIDE + s];
-                const float4* wv = reinterpret_cast<const float4*>(&s_w[r * KS + s][cg * 16]);
+            for (int k = 0; k < NX; ++k) xin[k] = row[k];
+#pragma unroll
+            for (int sx = 0; sx < KS; ++sx) {
+                const float4* wv = reinterpret_cast<const float4*>(&s_w[r * KS + sx][cg * 16]);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const float4 w4 = wv[q];
-                    acc[q * 4 + 0] = fmaf(v, w4.x, acc[q * 4 + 0]);
-                    acc[q * 4 + 1] = fmaf(v, w4.y, acc[q * 4 + 1]);
-                    acc[q * 4 + 2] = fmaf(v, w4.z, acc[q * 4 + 2]);
-                    acc[q * 4 + 3] = fmaf(v, w4.w, acc[q * 4 + 3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float v = xin[j * STRIDE + sx];
+                        acc[j][q * 4 + 0] = fmaf(v, w4.x, acc[j][q * 4 + 0]);
+                        acc[j][q * 4 + 1] = fmaf(v, w4.y, acc[j][q * 4 + 1]);
+                        acc[j][q * 4 + 2] = fmaf(v, w4.z, acc[j][q * 4 + 2]);
+                        acc[j][q * 4 + 3] = fmaf(v, w4.w, acc[j][q * 4 + 3]);
+                    }
                 }
             }
         }
     }
-    const int ho = ho0 + py, wo = wo0 + px;
-    if (ho >= Ho || wo >= Wo) return;
-    const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * 64 + cg * 16;
-    if (add) {
+    const int ho = ho0 + py;
+    if (ho >= Ho) return;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] += add[o + i];
-    }
-    if (vec) {
+    for (int j = 0; j < 4; ++j) {
+        const int wo = wo0 + px4 * 4 + j;
+        if (wo >= Wo) continue;
+        const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * 64 + cg * 16;
+        float a[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] += vec[(size_t)b * vec_stride + cg * 16 + i];
-    }
-    if (out_f32) {
+        for (int i = 0; i < 16; ++i) a[i] = acc[j][i];
+        if (add) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) out_f32[o + i] = acc[i];
-    } else {
-        uint4 v0, v1;
-        v0.x = pack_h2(acc[0], acc[1]);   v0.y = pack_h2(acc[2], acc[3]);
-        v0.z = pack_h2(acc[4], acc[5]);   v0.w = pack_h2(acc[6], acc[7]);
-        v1.x = pack_h2(acc[8], acc[9]);   v1.y = pack_h2(acc[10], acc[11]);
-        v1.z = pack_h2(acc[12], acc[13]); v1.w = pack_h2(acc[14], acc[15]);
-        uint4* op = reinterpret_cast<uint4*>(out_f16 + o);
-        op[0] = v0;
-        op[1] = v1;
+            for (int i = 0; i < 16; i += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(add + o + i);
+                a[i] += t4.x; a[i + 1] += t4.y; a[i + 2] += t4.z; a[i + 3] += t4.w;
+            }
+        }
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] += vec[(size_t)b * vec_stride + cg * 16 + i];
+        }
+        if (out_f32) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(out_f32 + o + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);
+        } else {
+            uint4 v0, v1;
+            v0.x = pack_h2(a[0], a[1]);   v0.y = pack_h2(a[2], a[3]);
+            v0.z = pack_h2(a[4], a[5]);   v0.w = pack_h2(a[6], a[7]);
+            v1.x = pack_h2(a[8], a[9]);   v1.y = pack_h2(a[10], a[11]);
+            v1.z = pack_h2(a[12], a[13]); v1.w = pack_h2(a[14], a[15]);
+            uint4* op = reinterpret_cast<uint4*>(out_f16 + o);
+            op[0] = v0;
+            op[1] = v1;
+        }
     }
 }
 
@@ -139,6 +197,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) plane_stats_kernel(const f16* __restrict__ x, float* __restrict__ partial,
                                                           unsigned int* __restrict__ counters, float* __restrict__ stats,
                                                           int HW, int C, int pix_per_cta) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_sum[8][64], s_sq[8][64];
     __shared__ bool s_last;
     const int b = blockIdx.z, grp = blockIdx.y, ngrp = gridDim.y, nslab = gridDim.x, slab = blockIdx.x;
@@ -191,6 +251,8 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const f16* __restri
                                                              const f16* __restrict__ skip, const float* __restrict__ vec,
                                                              int vec_stride, f16* __restrict__ y, int HW, int C,
                                                              size_t total_vec8) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total_vec8; i += (size_t)gridDim.x * blockDim.x) {
         const size_t e = i * 8;
         const int c = (int)(e % C);
@@ -228,54 +290,93 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const f16* __restri
 // Decoder.final_layer (modules_DANRA_conditional.py:503-509): InstanceNorm(ConvT out) -> Conv3x3(64 -> c_out) + bias, fp32 NCHW
 // result (eps_hat).  Cout is 1 (or a few): a 576-long reduction per pixel, not a GEMM.  The normalisation is applied on
 // the fly; zero padding applies to the *normalised* tensor, so out-of-image taps contribute nothing.
-// One warp per output pixel row segment: lane <-> channel pair; warp-reduce over 64 channels.
-__global__ void __launch_bounds__(256) tail_conv_kernel(const f16* __restrict__ x,      // [B,H,W,64] (un-normalised)
-                                                        const float* __restrict__ stats,  // [B][64][2]
+// CTA = 8 x 32 output pixels: the (8+2) x (32+2) x 64-channel input tile is staged in shared memory with cp.async (all
+// loads in flight at once; out-of-image pixels zero-filled).  Thread = (vertical strip of 8 output pixels) x (8 of the 64
+// channels): each normalised input vector (16 B) is read once and used by the up-to-3 output rows it touches, with the 72
+// weights of the thread's channels in registers; the 8 channel groups of a pixel sit in adjacent lanes and are combined
+// with 3 shuffles.  grid = (ceil(W/32), ceil(H/8), B), 256 threads.
+constexpr int TAIL_SMEM = 10 * 34 * 64 * 2;
+__global__ void __launch_bounds__(256) tail_conv_kernel(const f16* __restrict__ x,       // [B,H,W,64] (un-normalised)
+                                                        const float* __restrict__ stats,  // [B][64] x {mean, rstd}
                                                         const float* __restrict__ w,      // [c_out][64][3][3]
                                                         const float* __restrict__ bias, float* __restrict__ out,  // [B,c_out,H,W]
                                                         int H, int W, int c_out) {
-    __shared__ float s_w[9][64];
-    __shared__ float s_mean[64], s_rstd[64];
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) uint8_t tail_smem[];
+    f16* tile = reinterpret_cast<f16*>(tail_smem);     // [10][34][64]
     const int b = blockIdx.z;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < 64) {
-        const float* st = stats + ((size_t)b * 64 + threadIdx.x) * 2;
-        s_mean[threadIdx.x] = st[0];
-        s_rstd[threadIdx.x] = st[1];
+    const int w0 = blockIdx.x * 32, h0 = blockIdx.y * 8;
+    for (int i = threadIdx.x; i < 10 * 34 * 8; i += 256) {
+        const int ch8 = i & 7, pix = i >> 3;
+        const int iy = pix / 34, ix = pix - iy * 34;
+        const int hi = h0 - 1 + iy, wi = w0 - 1 + ix;
+        const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+        const f16* src = x + (((size_t)b * H + (ok ? hi : 0)) * W + (ok ? wi : 0)) * 64 + ch8 * 8;
+        cp_async16(tile + (size_t)pix * 64 + ch8 * 8, src, ok);
     }
+    cp_async_commit();
+    const int cgp = threadIdx.x & 7;                    // channels cgp*8 .. +7
+    const int lcol = threadIdx.x >> 3;                  // 0..31
+    const int wcol = w0 + lcol;
+    float mean[8], rstd[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float2 st = *reinterpret_cast<const float2*>(stats + ((size_t)b * 64 + cgp * 8 + c) * 2);
+        mean[c] = st.x;
+        rstd[c] = st.y;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
     for (int oc = 0; oc < c_out; ++oc) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < 9 * 64; i += 256) {
-            const int c = i & 63, tap = i >> 6;
-            s_w[tap][c] = w[((size_t)oc * 64 + c) * 9 + tap];
-        }
-        __syncthreads();
-        const int c = lane * 2;
-        const float m0 = s_mean[c], m1 = s_mean[c + 1], r0 = s_rstd[c], r1 = s_rstd[c + 1];
-        // CTA covers 8 rows x 32 cols of pixels; each warp one row, looping over the 32 columns
-        const int h = blockIdx.y * 8 + warp;
-        if (h < H) {
-            for (int wx = 0; wx < 32; ++wx) {
-                const int wcol = blockIdx.x * 32 + wx;
-                if (wcol >= W) break;
-                float acc = 0.f;
+        float wr[9][8];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) wr[tap][c] = __ldg(w + ((size_t)oc * 64 + cgp * 8 + c) * 9 + tap);
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+        for (int ir = 0; ir < 10; ++ir) {
+            const int hi = h0 - 1 + ir;
+            const bool rok = hi >= 0 && hi < H;
+#pragma unroll
+            for (int sx = 0; sx < 3; ++sx) {
+                const int wi = wcol + sx - 1;
+                const bool ok = rok && wi >= 0 && wi < W;   // zero padding applies to the NORMALISED tensor
+                const uint4 raw = *reinterpret_cast<const uint4*>(tile + ((size_t)(ir * 34 + lcol + sx)) * 64 + cgp * 8);
+                float v[8];
+                float2 t2;
+                t2 = unpack_h2(raw.x); v[0] = t2.x; v[1] = t2.y;
+                t2 = unpack_h2(raw.y); v[2] = t2.x; v[3] = t2.y;
+                t2 = unpack_h2(raw.z); v[4] = t2.x; v[5] = t2.y;
+                t2 = unpack_h2(raw.w); v[6] = t2.x; v[7] = t2.y;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = ok ? (v[c] - mean[c]) * rstd[c] : 0.f;
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const int hi = h + r - 1;
-                    if (hi < 0 || hi >= H) continue;
+                    const int orow = ir - r;  // output row (within the strip) that sees this input row through filter row r
+                    if (orow < 0 || orow >= 8) continue;
+                    float a = acc[orow];
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        const int wi = wcol + s - 1;
-                        if (wi < 0 || wi >= W) continue;
-                        const float2 v = __half22float2(
-                            *reinterpret_cast<const f162*>(x + (((size_t)b * H + hi) * W + wi) * 64 + c));
-                        acc = fmaf((v.x - m0) * r0, s_w[r * 3 + s][c], acc);
-                        acc = fmaf((v.y - m1) * r1, s_w[r * 3 + s][c + 1], acc);
-                    }
+                    for (int c = 0; c < 8; ++c) a = fmaf(v[c], wr[r * 3 + sx][c], a);
+                    acc[orow] = a;
                 }
-                acc = warp_sum(acc);
-                if (lane == 0) out[(((size_t)b * c_out + oc) * H + h) * W + wcol] = acc + bias[oc];
             }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float a = acc[i];
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            acc[i] = a;
+        }
+        if (cgp == 0 && wcol < W) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (h0 + i < H) out[(((size_t)b * c_out + oc) * H + h0 + i) * W + wcol] = acc[i] + bias[oc];
         }
     }
 }
@@ -319,6 +420,8 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
                                                                int* __restrict__ t_arr, int B, size_t n, size_t per_sample,
                                                                unsigned long long seed, unsigned long long sample_offset,
                                                                float noise_scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = *step_ptr;
     const float alpha = alphas[i], beta = betas[i], ahat = alpha_hat[i];
     const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(alpha));
@@ -351,6 +454,8 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
 }
 // Runs after the update (stream order): i <- i-1 and t[b] <- i-1 for the next UNet evaluation.
 __global__ void step_advance_kernel(int* step_ptr, int* t_arr, int B) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = *step_ptr - 1;
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x) t_arr[b] = i;
@@ -358,6 +463,8 @@ __global__ void step_advance_kernel(int* step_ptr, int* t_arr, int B) {
 }
 
 __global__ void fill_int_kernel(int* p, int v, int n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
