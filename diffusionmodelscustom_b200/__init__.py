@@ -7,6 +7,7 @@ sm_100a CUDA behind the C ABI of ``include/b200ddpm.h``); there is no eager/CPU 
 """
 from .modules import Decoder, DecoderBlock, DiffusionNet, Encoder, ImageSelfAttention, SinusoidalEmbedding, UNet  # noqa: F401
 from .diffusion import Diffusion, DiffusionUtils, DiffusionUtilsV2  # noqa: F401
+from .unet_ms import UNet_downscale  # noqa: F401
 
 __all__ = ["Encoder", "Decoder", "DecoderBlock", "DiffusionNet", "ImageSelfAttention", "SinusoidalEmbedding", "UNet",
-           "DiffusionUtils", "DiffusionUtilsV2", "Diffusion"]
+           "DiffusionUtils", "DiffusionUtilsV2", "Diffusion", "UNet_downscale"]

@@ -664,7 +664,8 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = h->alloc(&h->d_temb, (size_t)B * 2048))) break;
         const int ccond = cfg->has_lsm + cfg->has_topo + cfg->cond_channels;
         if ((rc = h->alloc(&h->d_cond_stack, (size_t)B * std::max(ccond, 1) * H * H))) break;
-        if ((rc = h->alloc(&h->d_cond_pre, (size_t)B * (H / 2) * (H / 2) * 64))) break;
+        const size_t pre_px = (cfg->family == B2D_FAMILY_D) ? (size_t)H * H : (size_t)(H / 2) * (H / 2);
+        if ((rc = h->alloc(&h->d_cond_pre, (size_t)B * pre_px * 64))) break;
         if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "stream create failed"); break; }
     } while (0);
     if (rc) {

@@ -249,6 +249,13 @@ class NativeModel(nn.Module):
         n = batch * hw.value * hw.value * c.value
         return buf[:n].reshape(batch, hw.value, hw.value, c.value).permute(0, 3, 1, 2).contiguous()
 
+    def _set_schedule(self, h, betas, alphas, alpha_hat):
+        skey = (betas.data_ptr(), int(betas._version), len(betas))
+        if skey != self._sched_key:
+            b, a, ah = (v.detach().to("cpu", torch.float32).contiguous() for v in (betas, alphas, alpha_hat))
+            N.check(N.lib().b2d_set_schedule(h, b.data_ptr(), a.data_ptr(), ah.data_ptr(), len(b)))
+            self._sched_key = skey
+
     def launch_count(self) -> int:
         return 0 if self._h is None else int(N.lib().b2d_last_launch_count(self._h))
 

@@ -203,7 +203,7 @@ def family_d_time_embedding(t, channels=256):
                       torch.cos(t.repeat(1, channels // 2) * inv_freq)], dim=-1)
 
 
-def family_d_forward(sd, x, t, y_lowres, interp_mode="bicubic", time_dim=256):
+def family_d_forward(sd, x, t, y_lowres, interp_mode="bicubic", time_dim=256, taps=None):
     """UNet_downscale.forward, unet_ms.py:148-179."""
     temb = family_d_time_embedding(t, time_dim)
     if y_lowres is not None:
@@ -234,10 +234,12 @@ def family_d_forward(sd, x, t, y_lowres, interp_mode="bicubic", time_dim=256):
     x4 = sa("sa3", down("down3", x3))
     x4 = _double_conv(sd, "bot1", x4)
     x4 = _double_conv(sd, "bot3", x4)
-    h = sa("sa4", up("up1", x4, x3))
-    h = sa("sa5", up("up2", h, x2))
-    h = sa("sa6", up("up3", h, x1))
-    return F.conv2d(h, sd["outc.weight"], sd["outc.bias"])
+    u1 = sa("sa4", up("up1", x4, x3))
+    u2 = sa("sa5", up("up2", u1, x2))
+    u3 = sa("sa6", up("up3", u2, x1))
+    if taps is not None:
+        taps.update(x1=x1, x2=x2, x3=x3, bot=x4, u1=u1, u2=u2, u3=u3)
+    return F.conv2d(u3, sd["outc.weight"], sd["outc.bias"])
 
 
 # --------------------------------------------------------------------------- sampling loop

@@ -26,3 +26,18 @@ def inputs_r(case, batch=None, device="cuda"):
                              has_cond=case["has_cond"], num_classes=case["num_classes"])
     dev = {k: (v.to(device) if v is not None else None) for k, v in inp.items()}
     return inp, dev
+
+
+def build_ours_d(case, device="cuda"):
+    net = P.UNet_downscale(c_in=case["c_in"], c_out=1, time_dim=256, interp_mode="bicubic", img_size=case["hw"], device=device)
+    sd = synth.synth_state_dict_d(case["c_in"], 1, seed=case["wseed"])
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    return net.to(device), sd
+
+
+def inputs_d(case, batch=None, device="cuda"):
+    B = batch or case["batch"]
+    inp = synth.synth_inputs(B, case["hw"], seed=case["iseed"], lowres=case["lowres"])
+    dev = {k: (v.to(device) if v is not None else None) for k, v in inp.items()}
+    return inp, dev

@@ -12,8 +12,8 @@ import torch
 from diffusionmodelscustom_b200 import DiffusionUtils, synth
 from oracle import ddpm_oracle as O
 from tests import gpu_util as G
-from tests.cases import R_CASES, SAMPLE_CASES
-from tests.model_util import build_ours_r, inputs_r
+from tests.cases import D_CASES, R_CASES, SAMPLE_CASES
+from tests.model_util import build_ours_d, build_ours_r, inputs_d, inputs_r
 
 pytestmark = pytest.mark.gpu
 EPS_TOL = 1e-2
@@ -129,3 +129,34 @@ def test_errors_are_python_exceptions():
         net(dev["x"], tt, None, None, None, dev["topo"])          # lsm required by construction
     with pytest.raises(RuntimeError):
         net(inp["x"], tt.cpu())                                   # CPU tensors: no fallback
+
+
+# ----------------------------------------------------------------------------------------------- Family D (cfg 4)
+@pytest.mark.parametrize("name", list(D_CASES))
+def test_family_d_eps_vs_reference_golden(name, golden_dir):
+    case = D_CASES[name]
+    gold = np.load(os.path.join(golden_dir, f"d_{name}.npz"))
+    net, _ = build_ours_d(case)
+    inp, dev = inputs_d(case)
+    for t in case["ts"]:
+        tt = torch.full((case["batch"],), t, dtype=torch.long, device="cuda")
+        eps = net(dev["x"], tt, dev["y_lowres"])
+        err = G.rel_l2(eps, gold[f"eps_t{t}"])
+        assert err < EPS_TOL, (name, t, err)
+
+
+def test_family_d_without_lowres_field_and_sampling_loop():
+    """y=None => zeros_like(x) is concatenated (unet_ms.py:158); and the CUDA-graph sampler drives Family D too."""
+    case = dict(D_CASES["downscale_32"], c_in=2)
+    net, sd = build_ours_d(case)
+    inp, dev = inputs_d(case)
+    t = torch.full((case["batch"],), 77, dtype=torch.long)
+    ref = O.family_d_forward(sd, inp["x"], t, None)
+    assert G.rel_l2(net(dev["x"], t.cuda(), None), ref) < EPS_TOL
+    T = 9
+    z = synth.step_noise(case["batch"], 1, case["hw"], T, seed=3)
+    x0 = DiffusionUtils(T, 1e-4, 0.02, "cuda").sample(dev["x"], net, cond_img=dev["y_lowres"], noise=z.cuda())
+    fn = lambda x, tt: O.family_d_forward(sd, x, tt, inp["y_lowres"])
+    x0_ref = O.sample(fn, inp["x"].clone(), T, 1e-4, 0.02, noise=z)
+    rmse = float((x0.cpu() - x0_ref).pow(2).mean().sqrt())
+    assert rmse <= RMSE_TOL * float(x0_ref.std())

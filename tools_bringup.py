@@ -68,5 +68,28 @@ def main():
             try_(f"model {name} simt={simt}", model)
 
 
+def family_d():
+    from tests.cases import D_CASES
+    from tests.model_util import build_ours_d, inputs_d
+    case = D_CASES["cfg4_downscale_64"]
+    for simt in (True, False):
+        def model():
+            net, sd = build_ours_d(case)
+            net.debug_simt_conv = simt
+            inp, dev = inputs_d(case)
+            t = torch.full((case["batch"],), 300, dtype=torch.long)
+            taps = {}
+            ref = O.family_d_forward(sd, inp["x"], t, inp["y_lowres"], taps=taps)
+            eps = net(dev["x"], t.cuda(), dev["y_lowres"])
+            torch.cuda.synchronize()
+            rep = {k: round(G.rel_l2(net.debug_read(k, case["batch"]), taps[k]), 5) for k in ("x1", "x2", "x3", "bot", "u1", "u2", "u3")}
+            rep["eps"] = round(G.rel_l2(eps, ref), 5)
+            return rep
+        try_(f"family D cfg4 simt={simt}", model)
+
+
 if __name__ == "__main__":
+    if "--d" in sys.argv:
+        family_d()
+        sys.exit(0)
     main()
