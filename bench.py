@@ -39,6 +39,7 @@ WORKLOADS = {
     "cfg1": ("cfg1_uncond_64", 4, 1.381e9),
     "cfg2": ("cfg2_lsmtopo_64", 64, 1.398e9),
     "cfg3": ("cfg3_full_128", 32, 12.527e9),
+    "cfg4": ("cfg4_downscale_64", 64, 17.75e9),      # Family D (UNet_downscale), low-res field 8x8 bicubic-upsampled
 }
 
 
@@ -86,13 +87,20 @@ def cpu_port_throughput(case_name, batch, steps, warmup, threads):
     """Oracle port (FP32 torch on CPU) of one reverse step, timed; samples/s = batch / (t_step * 999)."""
     from diffusionmodelscustom_b200 import synth
     from oracle import ddpm_oracle as O
-    from tests.cases import R_CASES
-    case = R_CASES[case_name]
+    from tests.cases import D_CASES, R_CASES
     torch.set_num_threads(threads)
-    sd = synth.synth_state_dict_r(case["c_in"], 1, case["num_classes"], (case["hw"],) * 2, case["has_lsm"], case["has_topo"],
-                                  seed=case["wseed"])
-    inp = synth.synth_inputs(batch, case["hw"], seed=case["iseed"], has_lsm=case["has_lsm"], has_topo=case["has_topo"],
-                             has_cond=case["has_cond"], num_classes=case["num_classes"])
+    if case_name in D_CASES:
+        case = D_CASES[case_name]
+        sd = synth.synth_state_dict_d(case["c_in"], 1, seed=case["wseed"])
+        inp = synth.synth_inputs(batch, case["hw"], seed=case["iseed"], lowres=case["lowres"])
+        model_fn = lambda x, t: O.family_d_forward(sd, x, t, inp["y_lowres"])
+    else:
+        case = R_CASES[case_name]
+        sd = synth.synth_state_dict_r(case["c_in"], 1, case["num_classes"], (case["hw"],) * 2, case["has_lsm"],
+                                      case["has_topo"], seed=case["wseed"])
+        inp = synth.synth_inputs(batch, case["hw"], seed=case["iseed"], has_lsm=case["has_lsm"], has_topo=case["has_topo"],
+                                 has_cond=case["has_cond"], num_classes=case["num_classes"])
+        model_fn = lambda x, t: O.family_r_forward(sd, x, t, inp["y"], inp["cond"], inp["lsm"], inp["topo"])
     betas, alphas, ahat = O.schedule_tables(T_STEPS, 1e-4, 0.02)
     x = inp["x"].clone()
     g = torch.Generator().manual_seed(1)
@@ -102,7 +110,7 @@ def cpu_port_throughput(case_name, batch, steps, warmup, threads):
             i = T_STEPS - 1 - k
             t0 = time.perf_counter()
             t = torch.full((batch,), i, dtype=torch.long)
-            eps = O.family_r_forward(sd, x, t, inp["y"], inp["cond"], inp["lsm"], inp["topo"])
+            eps = model_fn(x, t)
             x = O.posterior_update(x, eps, torch.randn(x.shape, generator=g), i, betas, alphas, ahat)
             if k >= warmup:
                 times.append(time.perf_counter() - t0)
@@ -146,17 +154,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    from tests.cases import R_CASES
-    case = R_CASES[case_name]
-    args.workload_desc = (f"{args.workload}: Family R DiffusionNet, {case['hw']}x{case['hw']}, c_in={case['c_in']} "
-                          f"(lsm={case['has_lsm']}, topo={case['has_topo']}, cond={case['has_cond']}, "
-                          f"classes={case['num_classes']}), per-GPU batch {batch}, T={T_STEPS} linear beta")
+    from tests.cases import D_CASES, R_CASES
+    is_d = case_name in D_CASES
+    case = D_CASES[case_name] if is_d else R_CASES[case_name]
+    if is_d:
+        args.workload_desc = (f"{args.workload}: Family D UNet_downscale, {case['hw']}x{case['hw']}, c_in={case['c_in']} (x + "
+                              f"{case['lowres']}x{case['lowres']} low-res field, bicubic), per-GPU batch {batch}, T={T_STEPS} linear beta")
+    else:
+        args.workload_desc = (f"{args.workload}: Family R DiffusionNet, {case['hw']}x{case['hw']}, c_in={case['c_in']} "
+                              f"(lsm={case['has_lsm']}, topo={case['has_topo']}, cond={case['has_cond']}, "
+                              f"classes={case['num_classes']}), per-GPU batch {batch}, T={T_STEPS} linear beta")
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
     import torch.distributed as dist
     from diffusionmodelscustom_b200 import DiffusionUtils
-    from tests.model_util import build_ours_r, inputs_r
+    from tests.model_util import build_ours_d, build_ours_r, inputs_d, inputs_r
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
@@ -164,8 +177,14 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    net, _ = build_ours_r(case, dev)
-    host, d = inputs_r(dict(case, iseed=case["iseed"] + rank), batch, dev)
+    if is_d:
+        net, _ = build_ours_d(case, dev)
+        host, d = inputs_d(dict(case, iseed=case["iseed"] + rank), batch, dev)
+        for dd in (host, d):     # Family D: the low-res field travels in the cond_img slot of the sampler
+            dd.update(cond=dd.pop("y_lowres"), lsm=None, topo=None, y=None)
+    else:
+        net, _ = build_ours_r(case, dev)
+        host, d = inputs_r(dict(case, iseed=case["iseed"] + rank), batch, dev)
     du = DiffusionUtils(T_STEPS, 1e-4, 0.02, dev, "linear")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
     gather = [torch.empty_like(d["x"]) for _ in range(world)] if world > 1 else None

@@ -146,6 +146,24 @@ class UNet_downscale(NativeModel):
         return x
 
     @torch.no_grad()
+    def native_sample_host(self, x_host, y, cond_img, lsm_cond, topo_cond, betas, alphas, alpha_hat, device, noise=None,
+                           seed=0, sample_offset=0, noise_scale=1.0):
+        self._bind(x_host)
+        B, _, H, _ = x_host.shape
+        device = torch.device(device)
+        h = self._ensure(B, H, device)
+        low = cond_img if cond_img is not None else y
+        hostc = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+        out, lowc, nz = hostc(x_host).clone(), hostc(low), hostc(noise)
+        ch, cw = (0, 0) if lowc is None else (lowc.shape[-2], lowc.shape[-1])
+        with torch.cuda.device(device):
+            self._set_schedule(h, betas, alphas, alpha_hat)
+            self._cond_key = None
+            N.check(N.lib().b2d_sample_host(h, out.data_ptr(), None, None, N.ptr(lowc), ch, cw, None, N.ptr(nz), int(seed),
+                                            int(sample_offset), float(noise_scale), B))
+        return out
+
+    @torch.no_grad()
     def profile_step(self, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=None, reps=5):
         import ctypes as C
         self._bind(x)
