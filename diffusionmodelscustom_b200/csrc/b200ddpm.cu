@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "common.cuh"
 #include "conv.cuh"
 #include "elementwise.cuh"
@@ -386,8 +387,16 @@ struct Builder {
         ops.meta(role + ".ln", "layernorm", 0, 4.0 * rows * C);
         ops.push_back([=](cudaStream_t st) { return layernorm_launch(x, g, b, xn, rows, C, st); });
         conv(xn, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkv", nullptr, nullptr, 0, 0);
-        ops.meta(role + ".sdpa", "flash_attn", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
-        ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
+        static const bool no_tc_attn = getenv("B2D_NO_TC_ATTN") != nullptr;
+        if (attn_tc_supported(L, C, heads) && !no_tc_attn) {
+            auto tmq = std::make_shared<AttnTcMaps>();
+            if (attn_tc_make_map(tmq.get(), qkv, B, L, C) != 0) { err = -1; return; }
+            ops.meta(role + ".sdpa", "attn_tc", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
+            ops.push_back([=](cudaStream_t st) { return attn_tc_launch(*tmq, ao, Bc, L, C, heads, st); });
+        } else {
+            ops.meta(role + ".sdpa", "flash_attn", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
+            ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
+        }
         if (!h->cfg.attn_ff) {
             conv(ao, hw, hw, C, out, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, final_act);
         } else {
@@ -652,6 +661,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
     do {
         if ((rc = conv_tc_init_attrs())) break;
         if ((rc = flash_attn_init_attrs())) break;
+        if ((rc = attn_tc_init_attrs())) break;
         const int B = cfg->max_batch, H = cfg->img_size;
         const size_t n = (size_t)B * cfg->c_hr * H * H;
         if ((rc = h->alloc(&h->d_t, B))) break;
@@ -996,6 +1006,12 @@ int b2d_op_layernorm(const void* x, const float* gamma, const float* beta, void*
 
 int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream) {
     B2D_TRY(flash_attn_init_attrs());
+    if (attn_tc_supported(L, C, heads) && getenv("B2D_NO_TC_ATTN") == nullptr) {
+        B2D_TRY(attn_tc_init_attrs());
+        AttnTcMaps tm;
+        B2D_TRY(attn_tc_make_map(&tm, (const f16*)qkv, B, L, C));
+        return attn_tc_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
+    }
     return flash_attn_launch((const f16*)qkv, (f16*)o, B, L, C, heads, as_stream(stream));
 }
 

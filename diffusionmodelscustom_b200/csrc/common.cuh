@@ -87,6 +87,10 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     f162 v = __floats2half2_rn(sat_h(a), sat_h(b));
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t pack_h2_nosat(float a, float b) {   // inputs known to be in [0, 1]
+    f162 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     f162 v = *reinterpret_cast<f162*>(&u);
     return __half22float2(v);
@@ -195,6 +199,42 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 columns: thread l writes 16 x 32-bit words to its own lane (row), consecutive columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 rows (lanes) x 16 fp16 packed two per 32-bit column (8 columns per K=16 step)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Generic UMMA smem descriptor: layout 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; byte offsets as in
+// cute::UMMA::SmemDescriptor (LBO/SBO meaning depends on the operand's major-ness, see attention_tc.cuh).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+// kind::f16 instruction descriptor with explicit B major-ness (1 = MN-major)
+__host__ __device__ constexpr uint32_t umma_idesc_f16_ex(int M, int N, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // UMMA shared-memory descriptor: K-major operand, 128-byte swizzle, rows of 64 f16 (=128 B), 8-row atoms 1024 B apart.
 // (cute::UMMA::SmemDescriptor: start>>4 @[0,14), LBO>>4 @[16,30), SBO>>4 @[32,46), version=1 @[46,48), layout=2 @[61,64))

@@ -419,7 +419,7 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 inline int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_b,
-                          const uint32_t* box) {
+                          const uint32_t* box, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled fn = get_encode_fn();
     B2D_CHECK(fn != nullptr, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t gd[5], gs[4];
@@ -431,7 +431,7 @@ inline int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint
         if (i < rank - 1) gs[i] = strides_b[i];
     }
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B2D_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
     return 0;
