@@ -104,6 +104,14 @@ struct Handle {
     int graph_nodes = 0;
     int64_t last_launches = 0;
     cudaStream_t own_stream = nullptr;
+    // Micro-batch splitting: at small per-GPU batches most launches are latency-bound and fill a fraction of the SMs, so
+    // the batch is cut into `kids.size()` contiguous sub-batches whose step programs run as CONCURRENT branches of the
+    // captured graph (fork/join with events).  Kids share the parent's packed weights and own their activations.
+    std::vector<Handle*> kids;
+    std::vector<int> kid_b0, kid_B;
+    bool is_kid = false;
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_join;
     struct Tap { const f16* p; int C, hw; };
     std::map<std::string, Tap> taps;  // named activations (NHWC f16) readable through b2d_debug_read
 
@@ -122,13 +130,26 @@ struct Handle {
         taps.clear();
         prog_B = 0;
     }
+    void free_kids() {
+        for (Handle* k : kids) delete k;
+        kids.clear();
+        kid_b0.clear();
+        kid_B.clear();
+    }
     ~Handle() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        free_kids();
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (auto e : ev_join) cudaEventDestroy(e);
         free_program();
         for (void* p : allocs) cudaFree(p);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
 };
+
+}  // namespace b2d
+struct b2d_handle : public b2d::Handle {};
+namespace b2d {
 
 // ------------------------------------------------------------------------------------------------ weight packing
 static const HostTensor* find(Handle* h, const std::string& k) {
@@ -597,9 +618,132 @@ static int build_program_r(Handle* h, int B) {
     return 0;
 }
 
+// Every kernel of the step asks for the same (maximum) shared-memory carve-out: consecutive kernels with different
+// L1/shared splits force the SMs to drain and reconfigure between launches, which costs microseconds per launch.
+template <typename K>
+static int set_carveout(K kern) {
+    B2D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    return 0;
+}
+static int init_uniform_carveout() {
+    static bool done = false;
+    if (done || getenv("B2D_NO_CARVEOUT")) return 0;
+    B2D_TRY(set_carveout(conv_tc_kernel<64, 4>));
+    B2D_TRY(set_carveout(conv_tc_kernel<64, 8>));
+    B2D_TRY(set_carveout(conv_tc_kernel<128, 3>));
+    B2D_TRY(set_carveout(conv_tc_kernel<128, 6>));
+    B2D_TRY(set_carveout(conv_simt_kernel));
+    B2D_TRY(set_carveout(layernorm_rows_kernel<64>));
+    B2D_TRY(set_carveout(layernorm_rows_kernel<128>));
+    B2D_TRY(set_carveout(layernorm_rows_kernel<256>));
+    B2D_TRY(set_carveout(layernorm_rows_kernel<512>));
+    B2D_TRY(set_carveout(flash_attn_kernel<16>));
+    B2D_TRY(set_carveout(flash_attn_kernel<32>));
+    B2D_TRY(set_carveout(flash_attn_kernel<64>));
+    B2D_TRY(set_carveout(flash_attn_kernel<128>));
+    B2D_TRY(set_carveout(attn_small_d_kernel<2>));
+    B2D_TRY(set_carveout(attn_small_d_kernel<4>));
+    B2D_TRY(set_carveout(attn_small_d_kernel<8>));
+    B2D_TRY(set_carveout(attn_tc_kernel));
+    B2D_TRY(set_carveout(temb_project_kernel));
+    B2D_TRY(set_carveout(stem_conv_kernel<8, 2>));
+    B2D_TRY(set_carveout(stem_conv_kernel<3, 1>));
+    B2D_TRY(set_carveout(plane_stats_kernel));
+    B2D_TRY(set_carveout(instnorm_apply_kernel));
+    B2D_TRY(set_carveout(tail_conv_kernel));
+    B2D_TRY(set_carveout(posterior_update_kernel));
+    B2D_TRY(set_carveout(step_advance_kernel));
+    B2D_TRY(set_carveout(fill_int_kernel));
+    B2D_TRY(set_carveout(bicubic_resize_kernel));
+    B2D_TRY(set_carveout(sample_stats_kernel));
+    B2D_TRY(set_carveout(groupnorm_apply_kernel));
+    B2D_TRY(set_carveout(maxpool2_kernel));
+    B2D_TRY(set_carveout(upsample_cat_kernel));
+    B2D_TRY(set_carveout(outc_kernel));
+    done = true;
+    return 0;
+}
+
+// Per-batch device buffers of a handle (parent or kid).
+static int init_batch_buffers(Handle* h) {
+    const b2d_config& c = h->cfg;
+    const int B = c.max_batch, H = c.img_size;
+    B2D_TRY(h->alloc(&h->d_t, B));
+    B2D_TRY(h->alloc(&h->d_y, B));
+    B2D_TRY(h->alloc(&h->d_step, 4));
+    B2D_TRY(h->alloc(&h->d_eps, (size_t)B * c.c_out * H * H));
+    B2D_TRY(h->alloc(&h->d_stats, STATS_CAPACITY_PER_SAMPLE * (size_t)B));
+    h->n_temb = TEMB_R_TOTAL;
+    B2D_TRY(h->alloc(&h->d_temb, (size_t)B * 2048));
+    const int ccond = c.has_lsm + c.has_topo + c.cond_channels;
+    B2D_TRY(h->alloc(&h->d_cond_stack, (size_t)B * std::max(ccond, 1) * H * H));
+    const size_t pre_px = (c.family == B2D_FAMILY_D) ? (size_t)H * H : (size_t)(H / 2) * (H / 2);
+    B2D_TRY(h->alloc(&h->d_cond_pre, (size_t)B * pre_px * 64));
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return fail(-2, "stream create failed");
+    return 0;
+}
+
+// Number of concurrent sub-batches for a batch of B (B2D_SPLIT in the environment overrides; sub-batches >= 8 samples).
+static int split_count(const Handle* h, int B) {
+    if (h->is_kid) return 1;
+    static const int env = getenv("B2D_SPLIT") ? atoi(getenv("B2D_SPLIT")) : 0;
+    int n = env > 0 ? env : 1;   // measured on B200: no gain at batch 64 (per-CTA latency, not grid size, paces the launches)
+    while (n > 1 && B / n < 8) n >>= 1;
+    return n < 1 ? 1 : n;
+}
+
+static int ensure_program(Handle* h, int B);
+
+static int ensure_kids(Handle* h, int B, int n) {
+    bool ok = (int)h->kids.size() == n;
+    for (int i = 0; ok && i < n; ++i) {
+        const int lo = (int)((long long)B * i / n), hi = (int)((long long)B * (i + 1) / n);
+        ok = h->kid_b0[i] == lo && h->kid_B[i] == hi - lo;
+    }
+    if (ok) return 0;
+    if (h->graph_exec) {
+        cudaGraphExecDestroy(h->graph_exec);
+        h->graph_exec = nullptr;
+    }
+    h->free_kids();
+    if (!h->ev_fork) B2D_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    while ((int)h->ev_join.size() < n) {
+        cudaEvent_t e;
+        B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_join.push_back(e);
+    }
+    for (int i = 0; i < n; ++i) {
+        const int lo = (int)((long long)B * i / n), hi = (int)((long long)B * (i + 1) / n);
+        Handle* k = new b2d_handle();
+        h->kids.push_back(k);
+        h->kid_b0.push_back(lo);
+        h->kid_B.push_back(hi - lo);
+        k->cfg = h->cfg;
+        k->cfg.max_batch = hi - lo;
+        k->num_sms = h->num_sms;
+        k->is_kid = true;
+        k->dev = h->dev;             // shared packed weights (owned by the parent)
+        k->weights_loaded = true;
+        B2D_TRY(init_batch_buffers(k));
+        B2D_TRY(ensure_program(k, hi - lo));
+    }
+    return 0;
+}
+
 static int ensure_program(Handle* h, int B) {
     B2D_CHECK(h->weights_loaded, "b2d_load_weights has not been called");
     B2D_CHECK(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch of the handle");
+    const int nsplit = split_count(h, B);
+    if (nsplit > 1) {
+        h->free_program();
+        B2D_TRY(ensure_kids(h, B, nsplit));
+        h->prog_B = B;
+        return 0;
+    }
+    if (!h->kids.empty()) {
+        h->free_kids();
+        h->prog_B = 0;
+    }
     if (h->prog_B == B) return 0;
     if (h->graph_exec) {
         cudaGraphExecDestroy(h->graph_exec);
@@ -631,7 +775,6 @@ static int run_step_ops(Handle* h, cudaStream_t st) {
 }  // namespace b2d
 
 using namespace b2d;
-struct b2d_handle : public b2d::Handle {};
 
 // ================================================================================================= C ABI
 extern "C" {
@@ -662,21 +805,11 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = conv_tc_init_attrs())) break;
         if ((rc = flash_attn_init_attrs())) break;
         if ((rc = attn_tc_init_attrs())) break;
+        if ((rc = init_uniform_carveout())) break;
         const int B = cfg->max_batch, H = cfg->img_size;
         const size_t n = (size_t)B * cfg->c_hr * H * H;
-        if ((rc = h->alloc(&h->d_t, B))) break;
-        if ((rc = h->alloc(&h->d_y, B))) break;
-        if ((rc = h->alloc(&h->d_step, 4))) break;
-        if ((rc = h->alloc(&h->d_eps, (size_t)B * cfg->c_out * H * H))) break;
+        if ((rc = init_batch_buffers(h))) break;
         if ((rc = h->alloc(&h->d_x_stage, n))) break;
-        if ((rc = h->alloc(&h->d_stats, STATS_CAPACITY_PER_SAMPLE * (size_t)B))) break;
-        h->n_temb = TEMB_R_TOTAL;
-        if ((rc = h->alloc(&h->d_temb, (size_t)B * 2048))) break;
-        const int ccond = cfg->has_lsm + cfg->has_topo + cfg->cond_channels;
-        if ((rc = h->alloc(&h->d_cond_stack, (size_t)B * std::max(ccond, 1) * H * H))) break;
-        const size_t pre_px = (cfg->family == B2D_FAMILY_D) ? (size_t)H * H : (size_t)(H / 2) * (H / 2);
-        if ((rc = h->alloc(&h->d_cond_pre, (size_t)B * pre_px * 64))) break;
-        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = fail(-2, "stream create failed"); break; }
     } while (0);
     if (rc) {
         delete h;
@@ -732,6 +865,19 @@ int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, con
     cudaStream_t st = as_stream(stream);
     const b2d_config& c = h->cfg;
     const int H = c.img_size;
+    if (!h->kids.empty()) {
+        const size_t plane = (size_t)H * H;
+        const size_t cond_per = (c.family == B2D_FAMILY_D) ? (size_t)c.cond_channels * cond_h * cond_w
+                                                           : (size_t)c.cond_channels * plane;
+        for (size_t i = 0; i < h->kids.size(); ++i) {
+            const int b0 = h->kid_b0[i];
+            B2D_TRY(b2d_set_conditioning(static_cast<b2d_handle*>(h->kids[i]), lsm ? lsm + b0 * plane : nullptr,
+                                         topo ? topo + b0 * plane : nullptr, cond ? cond + b0 * cond_per : nullptr, cond_h,
+                                         cond_w, y ? y + b0 : nullptr, h->kid_B[i], stream));
+        }
+        h->has_y = (y != nullptr);
+        return 0;
+    }
     if (y) {
         B2D_CHECK(c.num_classes > 0, "y given but the model has no label embedding");
         // int64 -> int32 on device
@@ -778,6 +924,24 @@ int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps
     B2D_CHECK(h && x && t_host && eps_out, "null argument");
     B2D_TRY(ensure_program(h, B));
     cudaStream_t st = as_stream(stream);
+    if (!h->kids.empty()) {
+        const size_t per_in = (size_t)h->cfg.c_hr * h->cfg.img_size * h->cfg.img_size;
+        const size_t per_out = (size_t)h->cfg.c_out * h->cfg.img_size * h->cfg.img_size;
+        B2D_CUDA(cudaEventRecord(h->ev_fork, st));
+        int64_t launches = 0;
+        for (size_t i = 0; i < h->kids.size(); ++i) {
+            Handle* k = h->kids[i];
+            const int b0 = h->kid_b0[i];
+            B2D_CUDA(cudaStreamWaitEvent(k->own_stream, h->ev_fork, 0));
+            B2D_TRY(b2d_forward(static_cast<b2d_handle*>(k), x + b0 * per_in, t_host + b0, eps_out + b0 * per_out, h->kid_B[i],
+                                k->own_stream));
+            B2D_CUDA(cudaEventRecord(h->ev_join[i], k->own_stream));
+            B2D_CUDA(cudaStreamWaitEvent(st, h->ev_join[i], 0));
+            launches += k->last_launches;
+        }
+        h->last_launches = launches;
+        return 0;
+    }
     std::vector<int> ti(B);
     for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
     B2D_CUDA(cudaMemcpyAsync(h->d_t, ti.data(), B * 4, cudaMemcpyHostToDevice, st));
@@ -801,29 +965,78 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
     B2D_CHECK(c.c_hr == c.c_out, "sampling needs c_out == c_hr");
     Handle::GraphKey key;
     key.B = B; key.x = x_inout; key.noise = noise; key.seed = seed; key.off = sample_offset; key.scale = noise_scale;
+    // parts: the handle itself, or its concurrent sub-batch kids
+    struct Part { Handle* ph; int b0, Bi; };
+    std::vector<Part> parts;
+    if (h->kids.empty()) parts.push_back({h, 0, B});
+    else for (size_t i = 0; i < h->kids.size(); ++i) parts.push_back({h->kids[i], h->kid_b0[i], h->kid_B[i]});
+    static const bool no_graph = getenv("B2D_NO_GRAPH") != nullptr;   // A/B: plain stream launches (PDL) instead of a graph
+    if (no_graph) {
+        const int T = h->T;
+        for (auto& p : parts) {
+            B2D_CUDA(launch_k(fill_int_kernel, dim3((p.Bi + 255) / 256), dim3(256), 0, st, p.ph->d_t, T - 1, p.Bi));
+            B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, p.ph->d_step, T - 1, 1));
+        }
+        int64_t launches = 0;
+        for (int i = T - 1; i >= 1; --i) {
+            for (auto& p : parts) {
+                float* xs = x_inout + (size_t)p.b0 * per_sample;
+                p.ph->cur_x = xs;
+                p.ph->cur_eps = p.ph->d_eps;
+                B2D_TRY(run_step_ops(p.ph, st));
+                const size_t ni = per_sample * p.Bi;
+                const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
+                B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, xs, p.ph->d_eps,
+                                  noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
+                                  p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
+                                  noise_scale, n));
+                B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, st, p.ph->d_step, p.ph->d_t, p.Bi));
+                launches += (int64_t)p.ph->step_ops.size() + 2;
+            }
+        }
+        h->last_launches = launches;
+        return 0;
+    }
     if (!h->graph_exec || !(key == h->graph_key)) {
         if (h->graph_exec) {
             cudaGraphExecDestroy(h->graph_exec);
             h->graph_exec = nullptr;
         }
-        // capture ONE reverse step; the step index lives in device memory so the same graph serves every i
+        // capture ONE reverse step; the step index lives in device memory so the same graph serves every i.
+        // Sub-batches are forked onto their own streams inside the capture => concurrent branches of the graph.
         cudaStream_t cs = h->own_stream;
-        h->cur_x = x_inout;
-        h->cur_eps = h->d_eps;
         B2D_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        auto tail_ops = [&]() -> int {
-            const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)h->num_sms * 8);
-            B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, cs, x_inout, h->d_eps, noise, h->d_alphas,
-                              h->d_betas, h->d_alpha_hat, h->d_step, h->d_t, B, n, per_sample, seed, sample_offset,
-                              noise_scale));
-            B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, cs, h->d_step, h->d_t, B));
+        auto body = [&]() -> int {
+            if (parts.size() > 1) B2D_CUDA(cudaEventRecord(h->ev_fork, cs));
+            for (size_t i = 0; i < parts.size(); ++i) {
+                Part& p = parts[i];
+                cudaStream_t si = (i == 0) ? cs : p.ph->own_stream;
+                if (i > 0) B2D_CUDA(cudaStreamWaitEvent(si, h->ev_fork, 0));
+                float* xs = x_inout + (size_t)p.b0 * per_sample;
+                p.ph->cur_x = xs;
+                p.ph->cur_eps = p.ph->d_eps;
+                B2D_TRY(run_step_ops(p.ph, si));
+                const size_t ni = per_sample * p.Bi;
+                const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
+                B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, si, xs, p.ph->d_eps,
+                                  noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
+                                  p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
+                                  noise_scale, n));
+                B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, si, p.ph->d_step, p.ph->d_t, p.Bi));
+                if (i > 0) {
+                    B2D_CUDA(cudaEventRecord(h->ev_join[i], si));
+                    B2D_CUDA(cudaStreamWaitEvent(cs, h->ev_join[i], 0));
+                }
+            }
             return 0;
         };
-        int rc = run_step_ops(h, cs);
-        if (rc == 0) rc = tail_ops();
+        int rc = body();
         cudaGraph_t graph = nullptr;
         cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-        if (rc) return rc;
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
         B2D_CUDA(ce);
         size_t nn = 0;
         cudaGraphGetNodes(graph, nullptr, &nn);
@@ -834,11 +1047,12 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
         h->graph_key = key;
     }
     const int T = h->T;
-    B2D_CUDA(launch_k(fill_int_kernel, dim3((B + 255) / 256), dim3(256), 0, st, h->d_t, T - 1, B));
-    B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, h->d_step, T - 1, 1));
-    B2D_CUDA(cudaGetLastError());
+    for (auto& p : parts) {
+        B2D_CUDA(launch_k(fill_int_kernel, dim3((p.Bi + 255) / 256), dim3(256), 0, st, p.ph->d_t, T - 1, p.Bi));
+        B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, p.ph->d_step, T - 1, 1));
+    }
     for (int i = T - 1; i >= 1; --i) B2D_CUDA(cudaGraphLaunch(h->graph_exec, st));
-    h->last_launches = (int64_t)h->graph_nodes * (T - 1) + 2;
+    h->last_launches = (int64_t)h->graph_nodes * (T - 1) + 2 * (int64_t)parts.size();
     return 0;
 }
 
@@ -904,6 +1118,8 @@ int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32
                      int32_t max_ops, int32_t* n_ops) {
     B2D_CHECK(h && x && t_host && out && n_ops && reps >= 1, "bad argument");
     B2D_TRY(ensure_program(h, B));
+    if (!h->kids.empty())   // split handle: profile the first sub-batch's program (its launches carry its own work figures)
+        return b2d_profile_step(static_cast<b2d_handle*>(h->kids[0]), x, t_host, h->kid_B[0], reps, out, max_ops, n_ops);
     cudaStream_t st = h->own_stream;
     std::vector<int> ti(B);
     for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
@@ -945,6 +1161,7 @@ int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32
 
 int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out) {
     B2D_CHECK(h && name && out_host, "null argument");
+    if (!h->kids.empty()) return fail(-1, "debug taps are only available on unsplit programs (batch < 16 or B2D_SPLIT=1)");
     auto it = h->taps.find(name);
     if (it == h->taps.end()) return fail(-3, std::string("no such tap: ") + name);
     const size_t n = (size_t)h->prog_B * it->second.hw * it->second.hw * it->second.C;
@@ -1053,7 +1270,7 @@ int b2d_op_posterior_update(float* x, const float* eps, const float* z, const fl
     // z (if given) is the noise of THIS step: bias the pointer so that noise + i*n lands on it
     const float* noise = z ? z - (size_t)i * n : nullptr;
     B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, x, eps, noise, alphas, betas, alpha_hat, d_step, nullptr, B, n,
-                                                    (size_t)per_sample, seed, sample_offset, noise_scale));
+                                                    (size_t)per_sample, seed, sample_offset, noise_scale, n));
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(st);
     cudaFree(d_step);

@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
                                                                const float* __restrict__ alpha_hat, int* __restrict__ step_ptr,
                                                                int* __restrict__ t_arr, int B, size_t n, size_t per_sample,
                                                                unsigned long long seed, unsigned long long sample_offset,
-                                                               float noise_scale) {
+                                                               float noise_scale, size_t noise_stride) {
     pdl_launch_dependents();
     pdl_wait();
     const int i = *step_ptr;
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
         float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i > 1) {
             if (noise) {
-                zv = reinterpret_cast<const float4*>(noise + (size_t)i * n)[v];
+                zv = reinterpret_cast<const float4*>(noise + (size_t)i * noise_stride)[v];   // noise_stride = elements per step
             } else {
                 const size_t e = v * 4;
                 const unsigned long long sample = sample_offset + e / per_sample;

@@ -17,6 +17,7 @@ ap.add_argument("--workload", default="cfg2")
 ap.add_argument("--batch", type=int, default=0)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--perop", default="")
+ap.add_argument("--sample-steps", type=int, default=0, help="also run a short reverse loop (posterior update kernel)")
 a = ap.parse_args()
 case_name, batch, _ = WORKLOADS[a.workload]
 batch = a.batch or batch
@@ -26,6 +27,10 @@ _, d = inputs_r(case, batch)
 t = torch.full((batch,), 500, dtype=torch.long, device="cuda")
 for _ in range(a.iters):
     eps = net(d["x"], t, d["y"], d["cond"], d["lsm"], d["topo"])
+if a.sample_steps:
+    from diffusionmodelscustom_b200 import DiffusionUtils
+    du = DiffusionUtils(a.sample_steps + 1, 1e-4, 0.02, "cuda")
+    du.sample(d["x"], net, d["y"], d["cond"], d["lsm"], d["topo"], seed=1)
 torch.cuda.synchronize()
 print("launches per step:", net.launch_count(), "finite:", bool(torch.isfinite(eps).all()))
 if a.perop:
