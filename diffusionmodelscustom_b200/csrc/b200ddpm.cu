@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "conv.cuh"
 #include "elementwise.cuh"
+#include "gemm_stream.cuh"
 
 namespace b2d {
 thread_local Status g_status;
@@ -384,8 +385,15 @@ struct Builder {
             ops.meta(role, h->cfg.debug_simt_conv ? "conv_simt" : "conv_tc", 2.0 * M * Nn * K,
                      2.0 * ((double)B * Hi * Wi * Cin + M * Nn * (residual ? 2 : 1) + Nn * K));
         }
+        static const bool no_stream = getenv("B2D_NO_STREAM_GEMM") != nullptr;
         if (h->cfg.debug_simt_conv) {
             ops.push_back([pl](cudaStream_t st) { return conv_launch_simt(pl->p, st); });
+        } else if (!no_stream && gemm_stream_supported(p, h->num_sms)) {
+            auto gp = std::make_shared<GemmStreamPlan>();
+            gp->p = p;
+            if (gemm_stream_plan_build(*gp, h->num_sms) != 0) { err = -1; return; }
+            ops.pending.klass = "gemm_stream";
+            ops.push_back([gp](cudaStream_t st) { return gemm_stream_launch(*gp, st); });
         } else {
             if (conv_plan_build(*pl, h->num_sms) != 0) { err = -1; return; }
             if (pl->ws_floats) {
@@ -805,6 +813,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = conv_tc_init_attrs())) break;
         if ((rc = flash_attn_init_attrs())) break;
         if ((rc = attn_tc_init_attrs())) break;
+        if ((rc = gemm_stream_init_attrs())) break;
         if ((rc = init_uniform_carveout())) break;
         const int B = cfg->max_batch, H = cfg->img_size;
         const size_t n = (size_t)B * cfg->c_hr * H * H;
@@ -1202,6 +1211,14 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (impl == 2 || (impl == 0 && gemm_stream_supported(p, sms) && getenv("B2D_NO_STREAM_GEMM") == nullptr)) {
+        B2D_CHECK(gemm_stream_supported(p, impl == 2 ? 0 : sms), "shape not eligible for the streaming GEMM");
+        B2D_TRY(gemm_stream_init_attrs());
+        GemmStreamPlan gp;
+        gp.p = p;
+        B2D_TRY(gemm_stream_plan_build(gp, sms));
+        return gemm_stream_launch(gp, as_stream(stream));
+    }
     B2D_TRY(conv_tc_init_attrs());
     B2D_TRY(conv_plan_build(pl, sms));
     float* ws = nullptr;

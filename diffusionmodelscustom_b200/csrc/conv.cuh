@@ -100,7 +100,8 @@ __host__ __device__ constexpr int conv_smem_bytes() {
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(CONV_TC_THREADS)
-    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+    conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvParams p) {
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* accum_full = bars + 2 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    uint64_t* res_full = bars + 2 * STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,6 +128,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmO);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                 mbar_init(&empty[i], 1);
             }
             mbar_init(accum_full, 1);
+            mbar_init(res_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -175,6 +179,25 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                         tma_load_5d(a_dst, &tmA, &full[stage], pw * p.Cin + cb * 64, w0 + dw, ph, h0 + dh, n0);
                     }
                     tma_load_2d(b_dst, &tmB, &full[stage], tap * p.Cin + cb * 64, nblk * BN);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+            // residual tile(s): extra ring slots that only the epilogue consumes; they land while the last MMAs run
+            if (p.residual != nullptr && p.splits == 1) {
+                mbar_arrive_expect_tx(res_full, (BN / 64) * CONV_A_BYTES);
+                for (int jb = 0; jb < BN / 64; ++jb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    void* dst = sA + stage * CONV_A_BYTES;
+                    if (p.convt) {
+                        const int ab = (nblk * BN) / p.CoutT;
+                        const int cb0 = (nblk * BN) - ab * p.CoutT + jb * 64;
+                        tma_load_5d(dst, &tmR, res_full, (ab & 1) * p.CoutT + cb0, w0, ab >> 1, h0, n0);
+                    } else {
+                        tma_load_4d(dst, &tmR, res_full, nblk * BN + jb * 64, w0, h0, n0);
+                    }
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -247,59 +270,80 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                        __uint_as_float(v[j + 3])));
             }
-        } else
+        } else {
+            // Coalesced epilogue: each thread (= output pixel) builds its 128-byte row of a 64-channel block in a
+            // 128B-swizzled staging tile (a free pipeline stage; the residual block, if any, was TMA-loaded into the same
+            // tile and is read by the same thread first), then one thread issues a TMA store of the whole block.
+            const int nr = n < p.B ? n : p.B - 1;                 // out-of-range rows are clipped by the store; keep reads in range
+            if (p.residual != nullptr) mbar_wait(res_full, 0);
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-            tmem_ld_wait();
-            if (valid) {
-                const int c0 = cbase + ch * 32;
-                float f[32];
+            for (int jb = 0; jb < BN / 64; ++jb) {
+                uint8_t* stg = sA + ((num_kb + jb) % STAGES) * CONV_A_BYTES;
+                uint4* srow = reinterpret_cast<uint4*>(stg + row * 128);
+                const int sw = row & 7;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int ch = jb * 2 + half;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                    tmem_ld_wait();
+                    const int c0 = cbase + ch * 32;
+                    float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (p.bias) {
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.bias) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
-                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
                     }
-                }
-                if (p.residual) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + obase + ch * 32);
+                    if (p.residual) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 r4 = srow[(half * 4 + j) ^ sw];
+                            float2 t;
+                            t = unpack_h2(r4.x); f[j * 8 + 0] += t.x; f[j * 8 + 1] += t.y;
+                            t = unpack_h2(r4.y); f[j * 8 + 2] += t.x; f[j * 8 + 3] += t.y;
+                            t = unpack_h2(r4.z); f[j * 8 + 4] += t.x; f[j * 8 + 5] += t.y;
+                            t = unpack_h2(r4.w); f[j * 8 + 6] += t.x; f[j * 8 + 7] += t.y;
+                        }
+                    }
+                    if (p.act) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
+                    }
+                    if (p.post_add) {
+                        const float* pa = p.post_add + (size_t)nr * p.post_stride + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(pa + j));
+                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const uint4 r4 = __ldg(rp + j);
-                        float2 t;
-                        t = unpack_h2(r4.x); f[j * 8 + 0] += t.x; f[j * 8 + 1] += t.y;
-                        t = unpack_h2(r4.y); f[j * 8 + 2] += t.x; f[j * 8 + 3] += t.y;
-                        t = unpack_h2(r4.z); f[j * 8 + 4] += t.x; f[j * 8 + 5] += t.y;
-                        t = unpack_h2(r4.w); f[j * 8 + 6] += t.x; f[j * 8 + 7] += t.y;
+                        uint4 o;
+                        o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
+                        o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
+                        o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
+                        o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
+                        srow[(half * 4 + j) ^ sw] = o;
                     }
                 }
-                if (p.act) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
-                }
-                if (p.post_add) {
-                    const float* pa = p.post_add + (size_t)n * p.post_stride + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(pa + j));
-                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                fence_proxy_async();                               // generic-proxy smem writes -> visible to the TMA engine
+                named_bar_sync(1, 128);                            // the four epilogue warps
+                if (threadIdx.x == 64) {
+                    if (p.convt) {
+                        const int ab = (nblk * BN) / p.CoutT;
+                        tma_store_5d(&tmO, stg, (ab & 1) * p.CoutT + cbase + jb * 64, w0, ab >> 1, h0, n0);
+                    } else {
+                        tma_store_4d(&tmO, stg, cbase + jb * 64, w0, h0, n0);
                     }
-                }
-                uint4* op = reinterpret_cast<uint4*>(p.out + obase + ch * 32);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint4 o;
-                    o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
-                    o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
-                    o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
-                    o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
-                    op[j] = o;
+                    tma_store_commit();
                 }
             }
+            if (threadIdx.x == 64) tma_store_wait_all();           // smem must outlive the bulk reads; writes done before exit
         }
     }
     if (p.splits > 1) {
@@ -440,7 +484,7 @@ inline int make_tmap_f16(CUtensorMap* tm, const void* base, int rank, const uint
 // A fully resolved convolution launch (tensor maps are encoded once; buffers never move).
 struct ConvPlan {
     ConvParams p;
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO, tmR;
     int bn = 0;
     int stages = 4;
     dim3 grid;
@@ -496,6 +540,23 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     uint64_t ws[1] = {K * 2};
     uint32_t wb[2] = {64, (uint32_t)bn};
     B2D_TRY(make_tmap_f16(&pl.tmB, p.w, 2, wd, ws, wb));
+    // output (and residual) tiles for the TMA-store epilogue: the 128-pixel tile is a dense box of the stored tensor
+    auto out_map = [&](CUtensorMap* tm, const void* base) -> int {
+        const uint64_t Co = p.CoutT, Wo = p.Wo, Ho = p.Ho;
+        if (p.convt) {   // stored tensor [B][2Ho][2Wo][Co] viewed as [n][h][a][w][(b,c)]
+            uint64_t dims[5] = {2 * Co, Wo, 2, Ho, B};
+            uint64_t str[4] = {2 * Co * 2, 2 * Wo * Co * 2, 4 * Wo * Co * 2, 4 * Ho * Wo * Co * 2};
+            uint32_t box[5] = {64, (uint32_t)p.TW, 1, (uint32_t)p.TH, (uint32_t)p.TN};
+            return make_tmap_f16(tm, base, 5, dims, str, box);
+        }
+        uint64_t dims[4] = {Co, Wo, Ho, B};
+        uint64_t str[3] = {Co * 2, Wo * Co * 2, Ho * Wo * Co * 2};
+        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        return make_tmap_f16(tm, base, 4, dims, str, box);
+    };
+    B2D_TRY(out_map(&pl.tmO, p.out));
+    if (p.residual) B2D_TRY(out_map(&pl.tmR, p.residual));
+    else pl.tmR = pl.tmO;
     pl.tc_ready = true;
     return 0;
 }
@@ -530,7 +591,7 @@ inline int conv_tc_launch_t(const ConvPlan& pl, cudaStream_t st) {
     attr[1].val.programmaticStreamSerializationAllowed = g_pdl_enabled;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    B2D_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, pl.tmA, pl.tmB, pl.p));
+    B2D_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, STAGES>, pl.tmA, pl.tmB, pl.tmO, pl.tmR, pl.p));
     return 0;
 }
 

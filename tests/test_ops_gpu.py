@@ -49,6 +49,33 @@ def test_conv_matches_torch(case, impl):
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
 
 
+STREAM_CASES = [  # B, H, Cin, Cout, convt
+    (2, 16, 64, 192, False), (3, 16, 128, 384, False), (5, 8, 64, 64, False), (2, 32, 128, 128, False),
+    (1, 19 * 0 + 16, 64, 256, False), (3, 8, 64, 64, True), (2, 16, 128, 128, True), (70, 32, 64, 192, False)]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=[f"B{c[0]}_H{c[1]}_K{c[2]}_N{c[3]}_{'convT' if c[4] else 'lin'}" for c in STREAM_CASES])
+def test_streaming_gemm_matches_torch(case):
+    """Persistent streaming GEMM (gemm_stream.cuh) incl. ragged last M tile, two K blocks, several N blocks, ConvT store,
+    residual + ReLU + per-sample vector epilogue."""
+    B, H, Cin, Cout, convt = case
+    g = torch.Generator().manual_seed(B * 1000 + Cin + Cout)
+    x = _bf(torch.randn(B, Cin, H, H, generator=g))
+    bias = torch.randn(Cout, generator=g)
+    if convt:
+        w = _bf(torch.randn(Cin, Cout, 2, 2, generator=g) / math.sqrt(Cin))
+        ref = F.conv_transpose2d(x, w, bias, stride=2)
+        out = G.conv2d(G.nhwc_f16(x), G.pack_convt_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, 1, 1, 0, convt=True, impl=2)
+    else:
+        w = _bf(torch.randn(Cout, Cin, 1, 1, generator=g) / math.sqrt(Cin))
+        res = _bf(torch.randn(B, Cout, H, H, generator=g))
+        vec = torch.randn(B, Cout, generator=g)
+        ref = F.relu(F.conv2d(x, w, bias) + res) + vec[:, :, None, None]
+        out = G.conv2d(G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), G.nhwc_f16(res), vec.cuda(), B, H, H, Cin, Cout, 1, 1, 0,
+                       act=1, impl=2)
+    assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
+
+
 @pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
 def test_conv_full_epilogue(impl):
     """bias -> +residual -> ReLU -> +per-sample channel vector (encoder stage tail) and GELU variant."""

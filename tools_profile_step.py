@@ -9,8 +9,8 @@ import torch
 
 sys.path.insert(0, ".")
 from bench import WORKLOADS                            # noqa: E402
-from tests.cases import R_CASES                        # noqa: E402
-from tests.model_util import build_ours_r, inputs_r    # noqa: E402
+from tests.cases import D_CASES, R_CASES               # noqa: E402
+from tests.model_util import build_ours_d, build_ours_r, inputs_d, inputs_r    # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2")
@@ -21,9 +21,15 @@ ap.add_argument("--sample-steps", type=int, default=0, help="also run a short re
 a = ap.parse_args()
 case_name, batch, _ = WORKLOADS[a.workload]
 batch = a.batch or batch
-case = R_CASES[case_name]
-net, _ = build_ours_r(case)
-_, d = inputs_r(case, batch)
+if case_name in D_CASES:
+    case = D_CASES[case_name]
+    net, _ = build_ours_d(case)
+    _, d = inputs_d(case, batch)
+    d.update(cond=d.pop("y_lowres"), lsm=None, topo=None, y=None)
+else:
+    case = R_CASES[case_name]
+    net, _ = build_ours_r(case)
+    _, d = inputs_r(case, batch)
 t = torch.full((batch,), 500, dtype=torch.long, device="cuda")
 for _ in range(a.iters):
     eps = net(d["x"], t, d["y"], d["cond"], d["lsm"], d["topo"])
