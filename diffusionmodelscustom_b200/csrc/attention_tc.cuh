@@ -22,6 +22,20 @@ namespace b2d {
 constexpr int ATC_BLK = 128;   // queries per CTA (UMMA M)
 constexpr int ATC_BN = 64;     // keys per block (UMMA N of S, K extent of P.V)
 constexpr int ATC_CTAS_PER_SM = 3;
+constexpr int ATC_POLY = 0;    // of every 8 fp16 pairs of P, this many are exponentiated on the FMA pipe (rest on the SFU)
+
+// 2^x on the FMA/ALU pipes (the SFU does 16 ex2/clk/SM and is what bounds this kernel): round-to-nearest split
+// x = n + f, f in [-0.5, 0.5] via the 1.5*2^23 magic constant, degree-3 minimax polynomial for 2^f (max rel. error 7.7e-5,
+// below the 4.9e-4 resolution of the fp16 P it feeds), exponent patched in with an integer add.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float xr = x + 12582912.0f;
+    const float f = x - (xr - 12582912.0f);
+    float p = fmaf(0.055088773f, f, 0.24260406f);
+    p = fmaf(p, f, 0.69327623f);
+    p = fmaf(p, f, 0.99992895f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
 constexpr int ATC_D = 16;
 constexpr int ATC_STAGES = 4;
 constexpr int ATC_TILE_BYTES = ATC_BLK * ATC_D * 2;   // Q tile, 4 KB
@@ -199,9 +213,12 @@ __global__ void __launch_bounds__(ATC_THREADS, ATC_CTAS_PER_SM) attn_tc_kernel(c
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    pk[ch][i] = pack_h2_nosat(ex2_approx(fmaf(__uint_as_float(v[ch][2 * i]), scale_log2e, -m_ref)),
-                                              ex2_approx(fmaf(__uint_as_float(v[ch][2 * i + 1]), scale_log2e, -m_ref)));
+                for (int i = 0; i < 16; ++i) {
+                    const float x0 = fmaf(__uint_as_float(v[ch][2 * i]), scale_log2e, -m_ref);
+                    const float x1 = fmaf(__uint_as_float(v[ch][2 * i + 1]), scale_log2e, -m_ref);
+                    pk[ch][i] = ((i & 7) < ATC_POLY) ? pack_h2_nosat(ex2_poly(x0), ex2_poly(x1))
+                                                     : pack_h2_nosat(ex2_approx(x0), ex2_approx(x1));
+                }
             }
             mbar_wait(&p_empty[0], (j & 1) ^ 1);                // P.V of block j-1 has finished reading the P buffer
             tc_fence_after();
