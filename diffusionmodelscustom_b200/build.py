@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200ddpm.so")
 SOURCES = ["b200ddpm.cu"]
-HEADERS = ["common.cuh", "conv.cuh", "attention.cuh", "attention_tc.cuh", "gemm_stream.cuh", "elementwise.cuh", "family_d.cuh",
+HEADERS = ["common.cuh", "conv.cuh", "attention.cuh", "attention_tc.cuh", "gemm_stream.cuh", "norm_fused.cuh", "elementwise.cuh", "family_d.cuh",
            os.path.join("..", "..", "include", "b200ddpm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -15,6 +15,7 @@
 #include "conv.cuh"
 #include "elementwise.cuh"
 #include "gemm_stream.cuh"
+#include "norm_fused.cuh"
 
 namespace b2d {
 thread_local Status g_status;
@@ -465,6 +466,19 @@ struct Builder {
             return 0;
         });
     }
+    // InstanceNorm (+skip +vec) in ONE launch when the (sample, 64-channel) slab fits a cluster's shared memory
+    bool instnorm_fused(const f16* x, const f16* skip, const float* vec, int vec_stride, f16* y, int hw, int C) {
+        static const bool off = getenv("B2D_NO_FUSED_NORM") != nullptr;
+        const int HW = hw * hw;
+        if (off || norm_fused_cluster(HW) == 0) return false;
+        NormParams np{};
+        np.x = x; np.y = y; np.add = skip; np.vec = vec; np.vec_stride = vec_stride; np.C = C; np.rows = HW;
+        np.slab_stride = (long long)HW * C;
+        const int Bc = B, groups = C / 64;
+        ops.meta("in_fused", "norm_fused", 0, 2.0 * B * HW * C * (skip ? 3 : 2));
+        ops.push_back([=](cudaStream_t s) { return norm_fused_launch<0>(np, Bc, groups, s); });
+        return true;
+    }
     void instnorm_apply(const f16* x, const float* st, const f16* skip, const float* vec, int vec_stride, f16* y, int hw,
                         int C) {
         const int HW = hw * hw;
@@ -586,15 +600,19 @@ static int build_program_r(Handle* h, int B) {
         const std::string r = "d" + std::to_string(i);
         f16* up = bd.act((size_t)B * hout * hout * ci);
         bd.conv(dcur, hin, hin, ci, up, ci, 1, 1, 0, true, r + ".up", nullptr, nullptr, 0, 0);
-        float* st1 = bd.stats_slice(ci);
-        bd.plane_stats(up, hout, ci, st1);
-        bd.instnorm_apply(up, st1, nullptr, nullptr, 0, up, hout, ci);
+        if (!bd.instnorm_fused(up, nullptr, nullptr, 0, up, hout, ci)) {
+            float* st1 = bd.stats_slice(ci);
+            bd.plane_stats(up, hout, ci, st1);
+            bd.instnorm_apply(up, st1, nullptr, nullptr, 0, up, hout, ci);
+        }
         f16* cv = bd.act((size_t)B * hout * hout * co);
         bd.conv(up, hout, hout, ci, cv, co, 3, 1, 1, false, r + ".conv", nullptr, nullptr, 0, 0);
-        float* st2 = bd.stats_slice(co);
-        bd.plane_stats(cv, hout, co, st2);
         f16* pre = bd.act((size_t)B * hout * hout * co);
-        bd.instnorm_apply(cv, st2, fmap[3 - i], temb + TEMB_DEC_OFF[i], TS, pre, hout, co);
+        if (!bd.instnorm_fused(cv, fmap[3 - i], temb + TEMB_DEC_OFF[i], TS, pre, hout, co)) {
+            float* st2 = bd.stats_slice(co);
+            bd.plane_stats(cv, hout, co, st2);
+            bd.instnorm_apply(cv, st2, fmap[3 - i], temb + TEMB_DEC_OFF[i], TS, pre, hout, co);
+        }
         f16* dout = bd.act((size_t)B * hout * hout * co);
         bd.attention(pre, hout, co, "da" + std::to_string(i), dout, 1 /*ReLU after attention, :459*/);
         h->taps["dec" + std::to_string(i) + "_pre"] = {pre, co, hout};
@@ -668,6 +686,10 @@ static int init_uniform_carveout() {
     B2D_TRY(set_carveout(maxpool2_kernel));
     B2D_TRY(set_carveout(upsample_cat_kernel));
     B2D_TRY(set_carveout(outc_kernel));
+    B2D_TRY(set_carveout(norm_fused_kernel<0>));
+    B2D_TRY(set_carveout(norm_fused_kernel<1>));
+    B2D_TRY(set_carveout(gemm_stream_kernel<1>));
+    B2D_TRY(set_carveout(gemm_stream_kernel<2>));
     done = true;
     return 0;
 }
@@ -814,6 +836,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = flash_attn_init_attrs())) break;
         if ((rc = attn_tc_init_attrs())) break;
         if ((rc = gemm_stream_init_attrs())) break;
+        if ((rc = norm_fused_init_attrs())) break;
         if ((rc = init_uniform_carveout())) break;
         const int B = cfg->max_batch, H = cfg->img_size;
         const size_t n = (size_t)B * cfg->c_hr * H * H;

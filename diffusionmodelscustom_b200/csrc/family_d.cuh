@@ -374,6 +374,31 @@ struct BuilderD : Builder {
             return 0;
         });
     }
+    // GroupNorm(1,C) statistics + affine (+residual, GELU, +emb) in ONE launch when a sample fits a cluster's shared memory
+    bool gn_fused(const f16* x, const std::string& gnrole, const f16* res, int act, const float* vec, int vec_stride, f16* y,
+                  size_t per_sample, int C) {
+        // measured on B200 (cfg4): the clustered one-pass kernel loses to the two-pass pair (4.28 vs 3.97 ms per step —
+        // 8-CTA clusters schedule poorly next to the other kernels of the graph), so it is opt-in for Family D
+        static const bool off = getenv("B2D_FUSED_GN") == nullptr;
+        const int rows = (int)(per_sample / 64);
+        if (off || norm_fused_cluster(rows) == 0) return false;
+        NormParams np{};
+        np.x = x; np.y = y; np.add = res; np.vec = vec; np.vec_stride = vec_stride; np.act = act; np.C = C; np.rows = rows;
+        np.gamma = W<float>(gnrole + ".g");
+        np.beta = W<float>(gnrole + ".b");
+        np.slab_stride = (long long)per_sample;
+        const int Bc = B;
+        ops.meta("gn_fused", "norm_fused", 0, 2.0 * B * per_sample * (res ? 3 : 2));
+        ops.push_back([=](cudaStream_t s) { return norm_fused_launch<1>(np, Bc, 1, s); });
+        return true;
+    }
+    void gn(const f16* x, const std::string& gnrole, const f16* res, int act, const float* vec, int vec_stride, f16* y,
+            size_t per_sample, int C) {
+        if (gn_fused(x, gnrole, res, act, vec, vec_stride, y, per_sample, C)) return;
+        float* st = stat2();
+        gn_stats(x, per_sample, st);
+        gn_apply(x, st, gnrole, res, act, vec, vec_stride, y, per_sample, C);
+    }
     float* stat2() {
         float* p = h->d_stats + h->stats_floats;
         h->stats_floats += (size_t)B * 2;
@@ -385,14 +410,10 @@ struct BuilderD : Builder {
         const size_t px = (size_t)hw * hw;
         f16* a = act(B * px * Cmid);
         conv(in, hw, hw, Cin, a, Cmid, 3, 1, 1, false, role + ".c1", nullptr, nullptr, 0, 0);
-        float* s1 = stat2();
-        gn_stats(a, px * Cmid, s1);
-        gn_apply(a, s1, role + ".gn1", nullptr, 2, nullptr, 0, a, px * Cmid, Cmid);
+        gn(a, role + ".gn1", nullptr, 2, nullptr, 0, a, px * Cmid, Cmid);
         f16* c = act(B * px * Cout);
         conv(a, hw, hw, Cmid, c, Cout, 3, 1, 1, false, role + ".c2", nullptr, nullptr, 0, 0);
-        float* s2 = stat2();
-        gn_stats(c, px * Cout, s2);
-        gn_apply(c, s2, role + ".gn2", residual ? in : nullptr, residual ? 2 : 0, vec, vec_stride, c, px * Cout, Cout);
+        gn(c, role + ".gn2", residual ? in : nullptr, residual ? 2 : 0, vec, vec_stride, c, px * Cout, Cout);
         return c;
     }
 };
@@ -438,14 +459,10 @@ static int build_program_d(Handle* h, int B) {
             return 0;
         });
     }
-    float* s1 = bd.stat2();
-    bd.gn_stats(a0, px0 * 64, s1);
-    bd.gn_apply(a0, s1, "inc.gn1", nullptr, 2, nullptr, 0, a0, px0 * 64, 64);
+    bd.gn(a0, "inc.gn1", nullptr, 2, nullptr, 0, a0, px0 * 64, 64);
     f16* x1 = bd.act(B * px0 * 64);
     bd.conv(a0, H, H, 64, x1, 64, 3, 1, 1, false, "inc.c2", nullptr, nullptr, 0, 0);
-    float* s2 = bd.stat2();
-    bd.gn_stats(x1, px0 * 64, s2);
-    bd.gn_apply(x1, s2, "inc.gn2", nullptr, 0, nullptr, 0, x1, px0 * 64, 64);
+    bd.gn(x1, "inc.gn2", nullptr, 0, nullptr, 0, x1, px0 * 64, 64);
     h->taps["x1"] = {x1, 64, H};
 
     auto down = [&](const f16* in, int hw_in, int Cin, int Cout, const std::string& role, int temb_off) -> f16* {
