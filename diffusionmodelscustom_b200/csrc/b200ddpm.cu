@@ -237,12 +237,42 @@ static int pack_linear(Handle* h, const std::string& role, const std::string& wk
     B2D_TRY(upload_f32(h, role + ".b", b->v));
     return 0;
 }
+// LayerNorm folded into the following Linear: W' = W * gamma (fp16), c1[n] = sum_k W'[n][k] (of the ROUNDED weights, so the
+// mean correction cancels exactly what the MMA accumulates), c2[n] = sum_k W[n][k] * beta[k] + b[n].
+static int pack_ln_linear(Handle* h, const std::string& role, const std::string& wkey, const std::string& bkey,
+                          const HostTensor* g, const HostTensor* be) {
+    NEED(w, wkey);
+    NEED(b, bkey);
+    const int N = (int)w->shape[0], K = (int)w->shape[1];
+    std::vector<uint16_t> p((size_t)N * K);
+    std::vector<float> c1(N), c2(N);
+    for (int n = 0; n < N; ++n) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const uint16_t hv = f2h(w->v[(size_t)n * K + k] * g->v[k]);
+            p[(size_t)n * K + k] = hv;
+            __half hh;
+            memcpy(&hh, &hv, 2);
+            s1 += (double)__half2float(hh);
+            s2 += (double)w->v[(size_t)n * K + k] * (double)be->v[k];
+        }
+        c1[n] = (float)s1;
+        c2[n] = (float)(s2 + (double)b->v[n]);
+    }
+    B2D_TRY(upload_f16(h, role + ".w", p));
+    B2D_TRY(upload_f32(h, role + ".c1", c1));
+    B2D_TRY(upload_f32(h, role + ".b", c2));
+    return 0;
+}
+
 static int pack_attention(Handle* h, const std::string& role, const std::string& prefix, const char* ln, const char* mha) {
     NEED(g, prefix + "." + ln + ".weight");
     NEED(b, prefix + "." + ln + ".bias");
     B2D_TRY(upload_f32(h, role + ".ln.g", g->v));
     B2D_TRY(upload_f32(h, role + ".ln.b", b->v));
     B2D_TRY(pack_linear(h, role + ".qkv", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias"));
+    if (g->v.size() <= 128)
+        B2D_TRY(pack_ln_linear(h, role + ".qkvln", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias", g, b));
     B2D_TRY(pack_linear(h, role + ".out", prefix + "." + mha + ".out_proj.weight", prefix + "." + mha + ".out_proj.bias"));
     if (h->cfg.attn_ff) {
         NEED(g2, prefix + ".ff_self.0.weight");
@@ -250,6 +280,8 @@ static int pack_attention(Handle* h, const std::string& role, const std::string&
         B2D_TRY(upload_f32(h, role + ".ffln.g", g2->v));
         B2D_TRY(upload_f32(h, role + ".ffln.b", b2->v));
         B2D_TRY(pack_linear(h, role + ".ff1", prefix + ".ff_self.1.weight", prefix + ".ff_self.1.bias"));
+        if (g2->v.size() <= 128)
+            B2D_TRY(pack_ln_linear(h, role + ".ff1ln", prefix + ".ff_self.1.weight", prefix + ".ff_self.1.bias", g2, b2));
         B2D_TRY(pack_linear(h, role + ".ff2", prefix + ".ff_self.3.weight", prefix + ".ff_self.3.bias"));
     }
     return 0;
@@ -357,6 +389,7 @@ struct Builder {
     }
 
     // GEMM-shaped op through the tcgen05 kernel (or the SIMT cross-check when cfg.debug_simt_conv)
+    const float* next_ln_c1 = nullptr;   // set right before conv(): fold a LayerNorm into this GEMM (stream path only)
     void conv(const f16* in, int Hi, int Wi, int Cin, f16* out, int Cout, int R, int stride, int pad, bool convt,
               const std::string& role, const f16* residual, const float* post_add, int post_stride, int act) {
         auto pl = std::make_shared<ConvPlan>();
@@ -380,7 +413,13 @@ struct Builder {
         p.post_stride = post_stride;
         p.act = act;
         p.out = out;
+        p.ln_c1 = next_ln_c1;
+        next_ln_c1 = nullptr;
         if (err) return;
+        if (p.ln_c1 && (h->cfg.debug_simt_conv || !gemm_stream_supported(p))) {
+            err = fail(-1, "internal: LayerNorm-folded GEMM requested for a shape the streaming GEMM does not take");
+            return;
+        }
         {
             const double M = (double)B * p.Ho * p.Wo, Nn = p.Cout, K = (double)R * R * Cin;
             ops.meta(role, h->cfg.debug_simt_conv ? "conv_simt" : "conv_tc", 2.0 * M * Nn * K,
@@ -389,7 +428,7 @@ struct Builder {
         static const bool no_stream = getenv("B2D_NO_STREAM_GEMM") != nullptr;
         if (h->cfg.debug_simt_conv) {
             ops.push_back([pl](cudaStream_t st) { return conv_launch_simt(pl->p, st); });
-        } else if (!no_stream && gemm_stream_supported(p, h->num_sms)) {
+        } else if (!no_stream && gemm_stream_supported(p)) {
             auto gp = std::make_shared<GemmStreamPlan>();
             gp->p = p;
             if (gemm_stream_plan_build(*gp, h->num_sms) != 0) { err = -1; return; }
@@ -414,9 +453,17 @@ struct Builder {
         const float* b = W<float>(role + ".ln.b");
         f16 *xn = s_xn, *qkv = s_qkv, *ao = s_ao;
         const int Bc = B;
-        ops.meta(role + ".ln", "layernorm", 0, 4.0 * rows * C);
-        ops.push_back([=](cudaStream_t st) { return layernorm_launch(x, g, b, xn, rows, C, st); });
-        conv(xn, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkv", nullptr, nullptr, 0, 0);
+        // LayerNorm folded into the QKV / FF1 GEMM whenever that GEMM runs on the streaming kernel (C <= 128, enough rows)
+        static const bool no_ln_fold = getenv("B2D_NO_LN_FOLD") != nullptr;
+        const bool fold = !no_ln_fold && !h->cfg.debug_simt_conv && !getenv("B2D_NO_STREAM_GEMM") && C <= 128 && rows >= GS_MIN_ROWS;
+        if (fold) {
+            next_ln_c1 = W<float>(role + ".qkvln.c1");
+            conv(x, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkvln", nullptr, nullptr, 0, 0);
+        } else {
+            ops.meta(role + ".ln", "layernorm", 0, 4.0 * rows * C);
+            ops.push_back([=](cudaStream_t st) { return layernorm_launch(x, g, b, xn, rows, C, st); });
+            conv(xn, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkv", nullptr, nullptr, 0, 0);
+        }
         static const bool no_tc_attn = getenv("B2D_NO_TC_ATTN") != nullptr;
         if (attn_tc_supported(L, C, heads) && !no_tc_attn) {
             auto tmq = std::make_shared<AttnTcMaps>();
@@ -435,9 +482,14 @@ struct Builder {
             conv(ao, hw, hw, C, mid, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, 0);
             const float* g2 = W<float>(role + ".ffln.g");
             const float* b2 = W<float>(role + ".ffln.b");
-            ops.meta(role + ".ffln", "layernorm", 0, 4.0 * rows * C);
-            ops.push_back([=](cudaStream_t st) { return layernorm_launch(mid, g2, b2, xn, rows, C, st); });
-            conv(xn, hw, hw, C, h1, C, 1, 1, 0, false, role + ".ff1", nullptr, nullptr, 0, 2);
+            if (fold) {
+                next_ln_c1 = W<float>(role + ".ff1ln.c1");
+                conv(mid, hw, hw, C, h1, C, 1, 1, 0, false, role + ".ff1ln", nullptr, nullptr, 0, 2);
+            } else {
+                ops.meta(role + ".ffln", "layernorm", 0, 4.0 * rows * C);
+                ops.push_back([=](cudaStream_t st) { return layernorm_launch(mid, g2, b2, xn, rows, C, st); });
+                conv(xn, hw, hw, C, h1, C, 1, 1, 0, false, role + ".ff1", nullptr, nullptr, 0, 2);
+            }
             conv(h1, hw, hw, C, out, C, 1, 1, 0, false, role + ".ff2", mid, nullptr, 0, final_act);
         }
     }
@@ -1234,8 +1286,8 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (impl == 2 || (impl == 0 && gemm_stream_supported(p, sms) && getenv("B2D_NO_STREAM_GEMM") == nullptr)) {
-        B2D_CHECK(gemm_stream_supported(p, impl == 2 ? 0 : sms), "shape not eligible for the streaming GEMM");
+    if (impl == 2 || (impl == 0 && gemm_stream_supported(p) && getenv("B2D_NO_STREAM_GEMM") == nullptr)) {
+        B2D_CHECK(gemm_stream_supported(p, impl == 2 ? 0 : GS_MIN_ROWS), "shape not eligible for the streaming GEMM");
         B2D_TRY(gemm_stream_init_attrs());
         GemmStreamPlan gp;
         gp.p = p;

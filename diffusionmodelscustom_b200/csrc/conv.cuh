@@ -35,6 +35,10 @@ struct ConvParams {
     int post_stride;
     int act;  // 0 none, 1 relu, 2 gelu(erf)
     f16* out;
+    // LayerNorm folded into the GEMM (gemm_stream only): A holds the UN-normalised rows, the weights are pre-scaled by gamma,
+    // out = rstd_m * (acc - mean_m * ln_c1[n]) + bias[n]  with ln_c1 = column sums of the scaled weights and
+    // bias = W beta + b.  Row statistics are computed by the epilogue threads from the A tile in shared memory.
+    const float* ln_c1;
     // split-K: gridDim.z = splits CTAs of one cluster share an output tile; fp32 partials go through `ws`
     int splits;
     float* ws;  // [tiles][splits][128][BN] fp32

@@ -6,7 +6,10 @@
 //     weights are TMA-loaded ONCE and stay resident in shared memory;
 //   * A tiles (128 rows x K) stream through a 4-6 stage TMA ring;
 //   * two TMEM accumulator stages: the MMA of tile i+1 is issued while the epilogue warps drain tile i
-//     (tcgen05.ld -> bias/residual/activation -> fp16 stores).
+//     (tcgen05.ld -> bias/residual/activation -> fp16 stores);
+//   * optional fused LayerNorm (ConvParams::ln_c1): the epilogue thread of row m reads that row of the A tile from shared
+//     memory (conflict-free in swizzle order), derives mean/rstd, and applies them algebraically to the accumulator, so the
+//     separate LayerNorm launch and its normalised copy of the activations disappear.
 // Same operand layouts, descriptors and epilogue semantics as conv_tc_kernel (conv.cuh).
 #pragma once
 #include "common.cuh"
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
         if (lane == 0) {
             for (int i = 0; i < STAGES; ++i) {
                 mbar_init(&a_full[i], 1);
-                mbar_init(&a_empty[i], 1);
+                mbar_init(&a_empty[i], p.ln_c1 ? 5 : 1);     // + the four epilogue warps when they read A for the LN statistics
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&t_full[i], 1);
@@ -139,6 +142,30 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
             const int m = m0 + row;
             const int mr = m < M ? m : M - 1;                 // rows past the end are clipped by the TMA store
             const int n = mr / HW;
+            float ln_mu = 0.f, ln_rstd = 1.f;
+            if (p.ln_c1 != nullptr) {
+                const int st = it % STAGES;
+                mbar_wait(&a_full[st], (it / STAGES) & 1);
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint4* arow = reinterpret_cast<const uint4*>(sA + (st * KB + kb) * CONV_A_BYTES + row * 128);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint4 a4 = arow[j ^ sw];          // swizzle order: conflict-free, and a sum does not care
+                        float2 tt;
+                        tt = unpack_h2(a4.x); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                        tt = unpack_h2(a4.y); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                        tt = unpack_h2(a4.z); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                        tt = unpack_h2(a4.w); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_empty[st]);
+                const float invk = 1.0f / (float)(KB * 64);
+                ln_mu = s1 * invk;
+                ln_rstd = rsqrtf(fmaxf(s2 * invk - ln_mu * ln_mu, 0.f) + 1e-5f);
+            }
             mbar_wait(&t_full[acc], (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -162,6 +189,16 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (p.ln_c1) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + c0 + j));
+                            f[j] = ln_rstd * (f[j] - ln_mu * c4.x);
+                            f[j + 1] = ln_rstd * (f[j + 1] - ln_mu * c4.y);
+                            f[j + 2] = ln_rstd * (f[j + 2] - ln_mu * c4.z);
+                            f[j + 3] = ln_rstd * (f[j + 3] - ln_mu * c4.w);
+                        }
+                    }
                     if (p.bias) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -242,13 +279,14 @@ struct GemmStreamPlan {
 };
 
 // Eligible: 1x1, stride 1 (incl. the ConvTranspose GEMM), K in {64, 128}, N a multiple of one of {256,192,128,64}, big M.
-inline bool gemm_stream_supported(const ConvParams& p, int num_sms) {
+constexpr int GS_MIN_ROWS = 8192;
+inline bool gemm_stream_supported(const ConvParams& p, int min_rows = GS_MIN_ROWS) {
     if (p.R != 1 || p.S != 1 || p.stride != 1 || p.pad != 0) return false;
     if (p.Cin != 64 && p.Cin != 128) return false;
     if (p.convt && p.residual) return false;
     if (p.convt && !(is_pow2(p.Ho) && is_pow2(p.Wo) && p.Wo <= 128)) return false;
     const long long M = (long long)p.B * p.Ho * p.Wo;
-    return M >= (long long)num_sms * 128 && p.Cout % 64 == 0;
+    return M >= min_rows && p.Cout % 64 == 0;
 }
 
 inline int gemm_stream_plan_build(GemmStreamPlan& pl, int num_sms) {

@@ -47,6 +47,20 @@ def test_family_r_eps_vs_oracle_batch5_mixed_t():
     assert G.rel_l2(eps2, ref[:2]) < EPS_TOL
 
 
+def test_family_r_batch8_streaming_gemm_with_folded_layernorm():
+    """B = 8 at 64x64 gives 8192 token rows at the C = 64 levels: the QKV projections run on the persistent streaming GEMM
+    with the LayerNorm folded in (row statistics from the A tile in shared memory); checked against the CPU oracle."""
+    case = dict(R_CASES["full_64_randbn"], batch=8, iseed=31)
+    net, sd = build_ours_r(case)
+    inp, dev = inputs_r(case)
+    t = torch.tensor([999, 3, 500, 42, 777, 1, 250, 640])
+    ref = O.family_r_forward(sd, inp["x"], t, inp["y"], inp["cond"], inp["lsm"], inp["topo"])
+    eps = net(dev["x"], t.cuda(), dev["y"], dev["cond"], dev["lsm"], dev["topo"])
+    assert G.rel_l2(eps, ref) < EPS_TOL
+    kinds = {p["klass"] for p in net.profile_step(dev["x"], t, dev["y"], dev["cond"], dev["lsm"], dev["topo"], reps=1)}
+    assert {"gemm_stream", "conv_tc", "attn_tc"} <= kinds
+
+
 def test_simt_and_tcgen05_programs_agree():
     case = R_CASES["cfg2_lsmtopo_64"]
     net, _ = build_ours_r(case)
@@ -143,6 +157,16 @@ def test_family_d_eps_vs_reference_golden(name, golden_dir):
         eps = net(dev["x"], tt, dev["y_lowres"])
         err = G.rel_l2(eps, gold[f"eps_t{t}"])
         assert err < EPS_TOL, (name, t, err)
+
+
+def test_family_d_batch8_folded_layernorms():
+    """Batch 8: C = 64 and C = 128 attention blocks (incl. their FF LayerNorm) take the LN-folded streaming GEMM."""
+    case = dict(D_CASES["cfg4_downscale_64"], batch=8, iseed=33)
+    net, sd = build_ours_d(case)
+    inp, dev = inputs_d(case)
+    t = torch.tensor([999, 3, 500, 42, 777, 1, 250, 640])
+    ref = O.family_d_forward(sd, inp["x"], t, inp["y_lowres"])
+    assert G.rel_l2(net(dev["x"], t.cuda(), dev["y_lowres"]), ref) < EPS_TOL
 
 
 def test_family_d_without_lowres_field_and_sampling_loop():
