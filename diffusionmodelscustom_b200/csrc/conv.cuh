@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
     uint64_t* accum_full = bars + 2 * STAGES;
     uint64_t* res_full = bars + 2 * STAGES + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+    __shared__ __align__(16) float s_bias[BN];   // bias of this N tile, staged while the main loop runs
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -256,6 +257,12 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
             pix = ((size_t)n * p.Ho + h) * (size_t)p.Wo + w;
         }
         const size_t obase = pix * (size_t)p.CoutT + cbase;
+        (void)obase;
+        {   // stage the bias slice of this tile in shared memory before the accumulator is ready
+            const int et = threadIdx.x - 64;
+            if (et < BN) s_bias[et] = p.bias ? __ldg(p.bias + cbase + et) : 0.f;
+            named_bar_sync(1, 128);
+        }
 
         mbar_wait(accum_full, 0);
         tc_fence_after();
@@ -295,10 +302,10 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (p.bias) {
+                    {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[ch * 32 + j]);
                             f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                         }
                     }
@@ -524,8 +531,8 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     p.splits = splits;
     pl.ws_floats = splits > 1 ? (size_t)tiles * splits * 128 * bn : 0;
     // deep pipelines for deep-K problems that leave SMs to spare anyway (the TMA round trip paces them)
-    pl.stages = (bn == 64) ? ((total_kb / splits >= 12 && tiles * splits <= num_sms) ? 8 : 4)
-                           : ((total_kb / splits >= 12 && tiles * splits <= num_sms) ? 6 : 3);
+    pl.stages = (bn == 64) ? ((total_kb / splits >= 6 && tiles * splits <= num_sms) ? 8 : 4)
+                           : ((total_kb / splits >= 5 && tiles * splits <= num_sms) ? 6 : 3);
     pl.grid = dim3(mtiles, p.Cout / bn, splits);
     const uint64_t C = p.Cin, W = p.Wi, H = p.Hi, B = p.B;
     if (p.stride == 1) {

@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const f16* __restri
 // weights of the thread's channels in registers; the 8 channel groups of a pixel sit in adjacent lanes and are combined
 // with 3 shuffles.  grid = (ceil(W/32), ceil(H/8), B), 256 threads.
 constexpr int TAIL_SMEM = 10 * 34 * 64 * 2;
-__global__ void __launch_bounds__(256) tail_conv_kernel(const f16* __restrict__ x,       // [B,H,W,64] (un-normalised)
+__global__ void __launch_bounds__(256, 2) tail_conv_kernel(const f16* __restrict__ x,       // [B,H,W,64] (un-normalised)
                                                         const float* __restrict__ stats,  // [B][64] x {mean, rstd}
                                                         const float* __restrict__ w,      // [c_out][64][3][3]
                                                         const float* __restrict__ bias, float* __restrict__ out,  // [B,c_out,H,W]
