@@ -123,7 +123,7 @@ def run_reference(args, rank, world):
         return
     case_name, _, _ = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    batch = 4
+    batch = 16          # bounded sample: large enough for the CPU GEMMs to thread well, small enough to finish in seconds
     t0 = time.perf_counter()
     sps, t_step = cpu_port_throughput(case_name, batch, max(args.steps, 1), max(args.warmup, 1), threads)
     sample = (f"{args.steps} timed reverse steps (after {max(args.warmup, 1)} warm-up) of the same network at batch {batch}, "

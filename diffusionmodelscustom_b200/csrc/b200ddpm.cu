@@ -265,7 +265,8 @@ static int pack_ln_linear(Handle* h, const std::string& role, const std::string&
     return 0;
 }
 
-static int pack_attention(Handle* h, const std::string& role, const std::string& prefix, const char* ln, const char* mha) {
+static int pack_attention(Handle* h, const std::string& role, const std::string& prefix, const char* ln, const char* mha,
+                          const char* ffp = "ff_self") {
     NEED(g, prefix + "." + ln + ".weight");
     NEED(b, prefix + "." + ln + ".bias");
     B2D_TRY(upload_f32(h, role + ".ln.g", g->v));
@@ -275,14 +276,14 @@ static int pack_attention(Handle* h, const std::string& role, const std::string&
         B2D_TRY(pack_ln_linear(h, role + ".qkvln", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias", g, b));
     B2D_TRY(pack_linear(h, role + ".out", prefix + "." + mha + ".out_proj.weight", prefix + "." + mha + ".out_proj.bias"));
     if (h->cfg.attn_ff) {
-        NEED(g2, prefix + ".ff_self.0.weight");
-        NEED(b2, prefix + ".ff_self.0.bias");
+        const std::string fp = prefix + "." + ffp;
+        NEED(g2, fp + ".0.weight");
+        NEED(b2, fp + ".0.bias");
         B2D_TRY(upload_f32(h, role + ".ffln.g", g2->v));
         B2D_TRY(upload_f32(h, role + ".ffln.b", b2->v));
-        B2D_TRY(pack_linear(h, role + ".ff1", prefix + ".ff_self.1.weight", prefix + ".ff_self.1.bias"));
-        if (g2->v.size() <= 128)
-            B2D_TRY(pack_ln_linear(h, role + ".ff1ln", prefix + ".ff_self.1.weight", prefix + ".ff_self.1.bias", g2, b2));
-        B2D_TRY(pack_linear(h, role + ".ff2", prefix + ".ff_self.3.weight", prefix + ".ff_self.3.bias"));
+        B2D_TRY(pack_linear(h, role + ".ff1", fp + ".1.weight", fp + ".1.bias"));
+        if (g2->v.size() <= 128) B2D_TRY(pack_ln_linear(h, role + ".ff1ln", fp + ".1.weight", fp + ".1.bias", g2, b2));
+        B2D_TRY(pack_linear(h, role + ".ff2", fp + ".3.weight", fp + ".3.bias"));
     }
     return 0;
 }
@@ -345,12 +346,16 @@ static int pack_family_r(Handle* h) {
     }
     B2D_TRY(upload_f32(h, "enc_inv", enc_inv));
     B2D_TRY(upload_f32(h, "dec_div", dec_div));
+    // two generations of ImageSelfAttention: modules_DANRA_conditional.py (keys attention.*, no FF) and
+    // DDPM_clean_application/src/unet.py (keys mha.*, ff.{0,1,3}.*); told apart by the keys present
+    const bool clean = find(h, E + "attention_layers.0.mha.in_proj_weight") != nullptr;
+    if (clean != (h->cfg.attn_ff != 0)) return fail(-3, "attn_ff of the config does not match the attention keys of the state_dict");
+    const char* mha = clean ? "mha" : "attention";
     for (int i = 0; i < 5; ++i)
-        B2D_TRY(pack_attention(h, "ea" + std::to_string(i), E + "attention_layers." + std::to_string(i), "layernorm",
-                               "attention"));
+        B2D_TRY(pack_attention(h, "ea" + std::to_string(i), E + "attention_layers." + std::to_string(i), "layernorm", mha, "ff"));
     for (int i = 0; i < 4; ++i) {
         const std::string p = D + "residual_layers." + std::to_string(i);
-        B2D_TRY(pack_attention(h, "da" + std::to_string(i), p + ".attention", "layernorm", "attention"));
+        B2D_TRY(pack_attention(h, "da" + std::to_string(i), p + ".attention", "layernorm", mha, "ff"));
         B2D_TRY(pack_convt(h, "d" + std::to_string(i) + ".up", p + ".transpose"));
         B2D_TRY(pack_conv(h, "d" + std::to_string(i) + ".conv", p + ".conv.weight", p + ".conv.bias", ""));
     }
@@ -390,6 +395,9 @@ struct Builder {
 
     // GEMM-shaped op through the tcgen05 kernel (or the SIMT cross-check when cfg.debug_simt_conv)
     const float* next_ln_c1 = nullptr;   // set right before conv(): fold a LayerNorm into this GEMM (stream path only)
+    bool want_gn_partial = false;        // set right before conv(): emit per-tile GroupNorm partial sums if the plan allows
+    const float* last_gn_partial = nullptr;   // result of that request, consumed by BuilderD::gn()
+    int last_gn_tps = 0, last_gn_ntiles = 0, last_gn_mtiles = 0;
     void conv(const f16* in, int Hi, int Wi, int Cin, f16* out, int Cout, int R, int stride, int pad, bool convt,
               const std::string& role, const f16* residual, const float* post_add, int post_stride, int act) {
         auto pl = std::make_shared<ConvPlan>();
@@ -415,6 +423,9 @@ struct Builder {
         p.out = out;
         p.ln_c1 = next_ln_c1;
         next_ln_c1 = nullptr;
+        const bool want_gn = want_gn_partial;
+        want_gn_partial = false;
+        last_gn_partial = nullptr;
         if (err) return;
         if (p.ln_c1 && (h->cfg.debug_simt_conv || !gemm_stream_supported(p))) {
             err = fail(-1, "internal: LayerNorm-folded GEMM requested for a shape the streaming GEMM does not take");
@@ -436,6 +447,17 @@ struct Builder {
             ops.push_back([gp](cudaStream_t st) { return gemm_stream_launch(*gp, st); });
         } else {
             if (conv_plan_build(*pl, h->num_sms) != 0) { err = -1; return; }
+            static const bool no_gn_epi = getenv("B2D_NO_GN_EPILOGUE") != nullptr;
+            if (want_gn && !no_gn_epi && pl->p.splits == 1 && pl->p.TN == 1 && !convt) {
+                const int mtiles = (int)pl->grid.x, ntiles = (int)pl->grid.y;
+                float* part = nullptr;
+                if (h->alloc(&part, (size_t)mtiles * ntiles * 2) != 0) { err = -2; return; }
+                pl->p.gn_partial = part;
+                last_gn_partial = part;
+                last_gn_tps = pl->p.tiles_w * pl->p.tiles_h;
+                last_gn_ntiles = ntiles;
+                last_gn_mtiles = mtiles;
+            }
             if (pl->ws_floats) {
                 if (h->alloc(&pl->p.ws, pl->ws_floats) != 0) { err = -2; return; }
             }

@@ -39,6 +39,9 @@ struct ConvParams {
     // out = rstd_m * (acc - mean_m * ln_c1[n]) + bias[n]  with ln_c1 = column sums of the scaled weights and
     // bias = W beta + b.  Row statistics are computed by the epilogue threads from the A tile in shared memory.
     const float* ln_c1;
+    // GroupNorm(1,C) statistics of the OUTPUT fused into the epilogue (conv_tc, unsplit, one sample per M tile): every CTA
+    // writes {sum, sum of squares} of its tile to gn_partial[(nblk * mtiles + mtile) * 2]; the consumer adds them in order.
+    float* gn_partial;
     // split-K: gridDim.z = splits CTAs of one cluster share an output tile; fp32 partials go through `ws`
     int splits;
     float* ws;  // [tiles][splits][128][BN] fp32
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
             // 128B-swizzled staging tile (a free pipeline stage; the residual block, if any, was TMA-loaded into the same
             // tile and is read by the same thread first), then one thread issues a TMA store of the whole block.
             const int nr = n < p.B ? n : p.B - 1;                 // out-of-range rows are clipped by the store; keep reads in range
+            float gs1 = 0.f, gs2 = 0.f;                           // GroupNorm partial sums of this thread's row
             if (p.residual != nullptr) mbar_wait(res_full, 0);
 #pragma unroll 1
             for (int jb = 0; jb < BN / 64; ++jb) {
@@ -332,6 +336,13 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                             f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                         }
                     }
+                    if (p.gn_partial != nullptr && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            gs1 += f[j];
+                            gs2 = fmaf(f[j], f[j], gs2);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 o;
@@ -352,6 +363,20 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                         tma_store_4d(&tmO, stg, cbase + jb * 64, w0, h0, n0);
                     }
                     tma_store_commit();
+                }
+            }
+            if (p.gn_partial != nullptr) {                         // block-reduce the tile's {sum, sumsq} in fixed order
+                gs1 = warp_sum(gs1);
+                gs2 = warp_sum(gs2);
+                if (lane == 0) {
+                    s_bias[2 * (warp - 2)] = gs1;                  // s_bias is dead by now: reuse as scratch
+                    s_bias[2 * (warp - 2) + 1] = gs2;
+                }
+                named_bar_sync(1, 128);
+                if (threadIdx.x == 64) {
+                    const size_t t = ((size_t)nblk * gridDim.x + blockIdx.x) * 2;
+                    p.gn_partial[t] = (s_bias[0] + s_bias[2]) + (s_bias[4] + s_bias[6]);
+                    p.gn_partial[t + 1] = (s_bias[1] + s_bias[3]) + (s_bias[5] + s_bias[7]);
                 }
             }
             if (threadIdx.x == 64) tma_store_wait_all();           // smem must outlive the bulk reads; writes done before exit

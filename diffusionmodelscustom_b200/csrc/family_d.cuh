@@ -102,18 +102,50 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const f16* __restrict
 }
 
 // y = act( (x - mean_b) * rstd_b * gamma_c + beta_c  (+ res) ) (+ vec[b][c]);  act: 0 none, 2 GELU(erf).
+// Statistics come either from stats[b] = {mean, rstd} (sample_stats_kernel) or from the per-tile {sum, sumsq} partials the
+// producing convolution wrote in its epilogue (gn_partial: [ntiles][mtiles][2], sample b owns m-tiles [b*tps, (b+1)*tps)):
+// every CTA of sample b adds them in the same fixed order.  grid = (chunks, B).
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const f16* __restrict__ x, const float* __restrict__ stats,
+                                                              const float* __restrict__ gn_partial, int tps, int ntiles, int mtiles,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
                                                               const f16* __restrict__ res, int act,
                                                               const float* __restrict__ vec, int vec_stride,
-                                                              f16* __restrict__ y, size_t per_sample, int C, size_t total8) {
+                                                              f16* __restrict__ y, size_t per_sample, int C) {
     pdl_launch_dependents();
     pdl_wait();
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total8; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = i * 8;
-        const int c = (int)(e % C);
-        const int b = (int)(e / per_sample);
-        const float mean = stats[b * 2], rstd = stats[b * 2 + 1];
+    __shared__ float s_ms[2];
+    const int b = blockIdx.y;
+    if (gn_partial != nullptr) {
+        if (threadIdx.x < 32) {
+            double ts = 0.0, tq = 0.0;
+            const int cnt = tps * ntiles;
+            for (int i = threadIdx.x; i < cnt; i += 32) {
+                const int nb = i / tps, mt = b * tps + (i - nb * tps);
+                ts += (double)__ldcg(gn_partial + ((size_t)nb * mtiles + mt) * 2);
+                tq += (double)__ldcg(gn_partial + ((size_t)nb * mtiles + mt) * 2 + 1);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ts += __shfl_xor_sync(0xffffffffu, ts, o);
+                tq += __shfl_xor_sync(0xffffffffu, tq, o);
+            }
+            if (threadIdx.x == 0) {
+                const double mean = ts / (double)per_sample;
+                const double var = fmax(tq / (double)per_sample - mean * mean, 0.0);
+                s_ms[0] = (float)mean;
+                s_ms[1] = (float)(1.0 / sqrt(var + 1e-5));
+            }
+        }
+    } else if (threadIdx.x == 0) {
+        s_ms[0] = stats[b * 2];
+        s_ms[1] = stats[b * 2 + 1];
+    }
+    __syncthreads();
+    const float mean = s_ms[0], rstd = s_ms[1];
+    const size_t n8 = per_sample / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = (size_t)b * per_sample + i * 8;
+        const int c = (int)((i * 8) % C);
         const uint4 xv = *reinterpret_cast<const uint4*>(x + e);
         float f[8];
         float2 t;
@@ -362,15 +394,17 @@ struct BuilderD : Builder {
         });
     }
     void gn_apply(const f16* x, const float* st, const std::string& gnrole, const f16* res, int act, const float* vec,
-                  int vec_stride, f16* y, size_t per_sample, int C) {
+                  int vec_stride, f16* y, size_t per_sample, int C, const float* partial = nullptr, int tps = 0,
+                  int ntiles = 0, int mtiles = 0) {
         const float* g = W<float>(gnrole + ".g");
         const float* b = W<float>(gnrole + ".b");
-        const size_t total8 = (size_t)B * per_sample / 8;
+        const size_t n8 = per_sample / 8;
+        const int Bc = B;
         ops.meta("gn_apply", "groupnorm_apply", 0, 2.0 * B * per_sample * (res ? 3 : 2));
         ops.push_back([=](cudaStream_t s) {
-            const int blocks = (int)std::min<size_t>((total8 + 255) / 256, (size_t)148 * 16);
-            B2D_CUDA(launch_k(groupnorm_apply_kernel, dim3(blocks), dim3(256), 0, s, x, st, g, b, res, act, vec, vec_stride, y,
-                              per_sample, C, total8));
+            int chunks = (int)std::min<size_t>((n8 + 255) / 256, (size_t)std::max(1, 148 * 16 / Bc));
+            B2D_CUDA(launch_k(groupnorm_apply_kernel, dim3(chunks, Bc), dim3(256), 0, s, x, st, partial, tps, ntiles, mtiles, g, b,
+                              res, act, vec, vec_stride, y, per_sample, C));
             return 0;
         });
     }
@@ -394,6 +428,13 @@ struct BuilderD : Builder {
     }
     void gn(const f16* x, const std::string& gnrole, const f16* res, int act, const float* vec, int vec_stride, f16* y,
             size_t per_sample, int C) {
+        if (last_gn_partial != nullptr) {   // the convolution that produced x already reduced it per tile
+            const float* part = last_gn_partial;
+            last_gn_partial = nullptr;
+            gn_apply(x, nullptr, gnrole, res, act, vec, vec_stride, y, per_sample, C, part, last_gn_tps, last_gn_ntiles,
+                     last_gn_mtiles);
+            return;
+        }
         if (gn_fused(x, gnrole, res, act, vec, vec_stride, y, per_sample, C)) return;
         float* st = stat2();
         gn_stats(x, per_sample, st);
@@ -409,9 +450,11 @@ struct BuilderD : Builder {
                      const float* vec, int vec_stride) {
         const size_t px = (size_t)hw * hw;
         f16* a = act(B * px * Cmid);
+        want_gn_partial = true;
         conv(in, hw, hw, Cin, a, Cmid, 3, 1, 1, false, role + ".c1", nullptr, nullptr, 0, 0);
         gn(a, role + ".gn1", nullptr, 2, nullptr, 0, a, px * Cmid, Cmid);
         f16* c = act(B * px * Cout);
+        want_gn_partial = true;
         conv(a, hw, hw, Cmid, c, Cout, 3, 1, 1, false, role + ".c2", nullptr, nullptr, 0, 0);
         gn(c, role + ".gn2", residual ? in : nullptr, residual ? 2 : 0, vec, vec_stride, c, px * Cout, Cout);
         return c;
@@ -461,6 +504,7 @@ static int build_program_d(Handle* h, int B) {
     }
     bd.gn(a0, "inc.gn1", nullptr, 2, nullptr, 0, a0, px0 * 64, 64);
     f16* x1 = bd.act(B * px0 * 64);
+    bd.want_gn_partial = true;
     bd.conv(a0, H, H, 64, x1, 64, 3, 1, 1, false, "inc.c2", nullptr, nullptr, 0, 0);
     bd.gn(x1, "inc.gn2", nullptr, 0, nullptr, 0, x1, px0 * 64, 64);
     h->taps["x1"] = {x1, 64, H};

@@ -52,6 +52,13 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = blockIdx.y;
     const int num_tiles = (M + 127) / 128;
+    __shared__ __align__(16) float s_bias[256], s_c1[256];   // bias / LN column sums of this CTA's N block (persistent => loaded once)
+    for (int i = threadIdx.x; i < NB; i += GS_THREADS) {
+        const int col = nblk * NB + i;
+        const int cb = p.convt ? col % p.CoutT : col;
+        s_bias[i] = p.bias ? __ldg(p.bias + cb) : 0.f;
+        s_c1[i] = p.ln_c1 ? __ldg(p.ln_c1 + cb) : 0.f;
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -189,20 +196,21 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                     float f[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    const int lc = jb * 64 + half * 32;             // column within this CTA's N block
                     if (p.ln_c1) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + c0 + j));
+                            const float4 c4 = *reinterpret_cast<const float4*>(&s_c1[lc + j]);
                             f[j] = ln_rstd * (f[j] - ln_mu * c4.x);
                             f[j + 1] = ln_rstd * (f[j + 1] - ln_mu * c4.y);
                             f[j + 2] = ln_rstd * (f[j + 2] - ln_mu * c4.z);
                             f[j + 3] = ln_rstd * (f[j + 3] - ln_mu * c4.w);
                         }
                     }
-                    if (p.bias) {
+                    {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + j));
+                            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[lc + j]);
                             f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                         }
                     }

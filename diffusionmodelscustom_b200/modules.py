@@ -275,19 +275,25 @@ class DiffusionNet(NativeModel):
     def _config(self, img_size, max_batch):
         e, d = self.encoder, self.decoder
         return N.Config(family=N.FAMILY_R, img_size=img_size, max_batch=max_batch, c_hr=e.hr_channels,
-                        c_out=d.output_channels, has_lsm=int(hasattr(e, "lsm")), has_topo=int(hasattr(e, "elevation")),
+                        c_out=d.output_channels, has_lsm=int(self._has_lsm()), has_topo=int(self._has_topo()),
                         cond_channels=e.cond_channels, num_classes=e.num_classes or 0, n_heads=e.n_heads, attn_ff=0,
                         debug_simt_conv=int(self.debug_simt_conv))
 
+    def _has_lsm(self):
+        # modules_DANRA_conditional.py:228 (hasattr(self,'lsm')) / src/unet.py:232 (cond_on_lsm => lsm_cond is passed)
+        return hasattr(self.encoder, "lsm") or getattr(self.encoder, "cond_on_lsm", False)
+
+    def _has_topo(self):
+        return hasattr(self.encoder, "elevation") or getattr(self.encoder, "cond_on_topo", False)
+
     def _set_conditioning(self, h, B, y, cond_img, lsm_cond, topo_cond, stream):
-        e = self.encoder
-        lsm = self._f32c(lsm_cond, "lsm_cond") if hasattr(e, "lsm") else None
-        topo = self._f32c(topo_cond, "topo_cond") if hasattr(e, "elevation") else None
+        lsm = self._f32c(lsm_cond, "lsm_cond") if self._has_lsm() else None
+        topo = self._f32c(topo_cond, "topo_cond") if self._has_topo() else None
         cond = self._f32c(cond_img, "cond_img")
-        if hasattr(e, "lsm") and lsm is None:
-            raise ValueError("model was built with lsm_tensor: lsm_cond is required")
-        if hasattr(e, "elevation") and topo is None:
-            raise ValueError("model was built with topo_tensor: topo_cond is required")
+        if self._has_lsm() and lsm is None:
+            raise ValueError("model was built with lsm conditioning: lsm_cond is required")
+        if self._has_topo() and topo is None:
+            raise ValueError("model was built with topography conditioning: topo_cond is required")
         yy = None
         if y is not None:
             if not y.is_cuda:
@@ -359,9 +365,8 @@ class DiffusionNet(NativeModel):
             return t.detach().to(dt).contiguous()
 
         out = hostc(x_host).clone()
-        e = self.encoder
-        lsm = hostc(lsm_cond) if hasattr(e, "lsm") else None
-        topo = hostc(topo_cond) if hasattr(e, "elevation") else None
+        lsm = hostc(lsm_cond) if self._has_lsm() else None
+        topo = hostc(topo_cond) if self._has_topo() else None
         cond, yy, nz = hostc(cond_img), hostc(y, torch.int64), hostc(noise)
         with torch.cuda.device(device):
             self._set_schedule(h, betas, alphas, alpha_hat)

@@ -56,7 +56,7 @@ def _bn(sd, g, prefix, c, randomize):
     sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
 
 
-def _attn(sd, g, prefix, c, ff=False, ln_name="layernorm", mha_name="attention", randomize=True):
+def _attn(sd, g, prefix, c, ff=False, ln_name="layernorm", mha_name="attention", randomize=True, ff_name="ff_self"):
     # LayerNorm affine is randomised a little so that gamma/beta handling is exercised
     sd[f"{prefix}.{ln_name}.weight"] = 1.0 + (0.1 * torch.randn(c, generator=g) if randomize else 0)
     sd[f"{prefix}.{ln_name}.bias"] = (0.05 * torch.randn(c, generator=g)) if randomize else torch.zeros(c)
@@ -66,15 +66,15 @@ def _attn(sd, g, prefix, c, ff=False, ln_name="layernorm", mha_name="attention",
     sd[f"{prefix}.{mha_name}.out_proj.weight"] = w
     sd[f"{prefix}.{mha_name}.out_proj.bias"] = 0.02 * torch.randn(c, generator=g)
     if ff:
-        sd[f"{prefix}.ff_self.0.weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
-        sd[f"{prefix}.ff_self.0.bias"] = 0.05 * torch.randn(c, generator=g)
-        sd[f"{prefix}.ff_self.1.weight"], sd[f"{prefix}.ff_self.1.bias"] = _linear(g, c, c)
-        sd[f"{prefix}.ff_self.3.weight"], sd[f"{prefix}.ff_self.3.bias"] = _linear(g, c, c)
+        sd[f"{prefix}.{ff_name}.0.weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        sd[f"{prefix}.{ff_name}.0.bias"] = 0.05 * torch.randn(c, generator=g)
+        sd[f"{prefix}.{ff_name}.1.weight"], sd[f"{prefix}.{ff_name}.1.bias"] = _linear(g, c, c)
+        sd[f"{prefix}.{ff_name}.3.weight"], sd[f"{prefix}.{ff_name}.3.bias"] = _linear(g, c, c)
 
 
 def synth_state_dict_r(c_in_total: int, c_out: int = 1, num_classes=None, img_hw=None,
                        has_lsm=False, has_topo=False, time_embedding: int = 256,
-                       seed: int = 42, randomize_bn: bool = False):
+                       seed: int = 42, randomize_bn: bool = False, clean: bool = False):
     """Family R (``DiffusionNet(Encoder, Decoder)``) state_dict with reference keys.
 
     c_in_total counts x channels + lsm + topo + cond image channels (what ``conv1`` sees,
@@ -83,9 +83,11 @@ def synth_state_dict_r(c_in_total: int, c_out: int = 1, num_classes=None, img_hw
     g = torch.Generator().manual_seed(seed)
     sd = OrderedDict()
     E = "encoder."
-    if has_lsm:
+    # clean=True: the DDPM_clean_application/src/unet.py generation — no lsm/elevation buffers, attention = mha/layernorm/ff
+    akw = dict(ff=True, mha_name="mha", ff_name="ff") if clean else {}
+    if has_lsm and not clean:
         sd[E + "lsm"] = torch.zeros(1, *img_hw)
-    if has_topo:
+    if has_topo and not clean:
         sd[E + "elevation"] = torch.zeros(1, *img_hw)
     sd[E + "conv1.weight"] = _xavier_conv(g, 64, c_in_total, 8, 8)
     _bn(sd, g, E + "bn1", 64, randomize_bn)
@@ -107,14 +109,14 @@ def synth_state_dict_r(c_in_total: int, c_out: int = 1, num_classes=None, img_hw
         sd[f"{E}time_projection_layers.{i}.1.weight"] = w
         sd[f"{E}time_projection_layers.{i}.1.bias"] = b
     for i, ch in enumerate(ENC_CH):
-        _attn(sd, g, f"{E}attention_layers.{i}", ch)
+        _attn(sd, g, f"{E}attention_layers.{i}", ch, **akw)
     sd[E + "conv2.weight"] = _xavier_conv(g, 64, 64, 8, 8)
     if num_classes is not None:
         sd[E + "label_emb.weight"] = torch.randn(num_classes, time_embedding, generator=g)
     D = "decoder."
     for i, (ci, co) in enumerate(DEC_IO):
         p = f"{D}residual_layers.{i}."
-        _attn(sd, g, p + "attention", co)
+        _attn(sd, g, p + "attention", co, **akw)
         w, b = _linear(g, co, time_embedding)
         sd[p + "time_projection_layer.1.weight"] = w
         sd[p + "time_projection_layer.1.bias"] = b

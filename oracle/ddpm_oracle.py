@@ -54,7 +54,7 @@ def posterior_update(x, eps, z, i, betas, alphas, alpha_hat):
 
 
 # --------------------------------------------------------------------------- shared pieces
-def image_self_attention(sd, p, x, n_heads, ln="layernorm", mha="attention", ff=False):
+def image_self_attention(sd, p, x, n_heads, ln="layernorm", mha="attention", ff=False, ffp="ff_self"):
     """modules_DANRA_conditional.py:91-110 (ImageSelfAttention) / unet_ms.py:21-27 (SelfAttention, ff=True);
     formulas verified against nn.MultiheadAttention in SURVEY.md Appendix A."""
     N, C, H, W = x.shape
@@ -74,9 +74,9 @@ def image_self_attention(sd, p, x, n_heads, ln="layernorm", mha="attention", ff=
     o = o.permute(0, 2, 1, 3).reshape(N, L, C)
     o = o @ sd[f"{p}.{mha}.out_proj.weight"].t() + sd[f"{p}.{mha}.out_proj.bias"] + tok
     if ff:
-        h = F.layer_norm(o, (C,), sd[f"{p}.ff_self.0.weight"], sd[f"{p}.ff_self.0.bias"], 1e-5)
-        h = F.gelu(h @ sd[f"{p}.ff_self.1.weight"].t() + sd[f"{p}.ff_self.1.bias"])
-        o = h @ sd[f"{p}.ff_self.3.weight"].t() + sd[f"{p}.ff_self.3.bias"] + o
+        h = F.layer_norm(o, (C,), sd[f"{p}.{ffp}.0.weight"], sd[f"{p}.{ffp}.0.bias"], 1e-5)
+        h = F.gelu(h @ sd[f"{p}.{ffp}.1.weight"].t() + sd[f"{p}.{ffp}.1.bias"])
+        o = h @ sd[f"{p}.{ffp}.3.weight"].t() + sd[f"{p}.{ffp}.3.bias"] + o
     return o.permute(0, 2, 1).reshape(N, C, H, W)
 
 
@@ -125,8 +125,15 @@ def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=N
     """DiffusionNet.forward (modules_DANRA_conditional.py:597-616) = Decoder(*Encoder(...), t).
 
     has_lsm/has_topo mirror ``hasattr(self,'lsm')`` / ``hasattr(self,'elevation')`` (:228-233) and
-    default to the presence of the registered buffers in the state_dict."""
+    default to the presence of the registered buffers in the state_dict.  A state_dict of the newer generation
+    (DDPM_clean_application/src/unet.py: attention keys ``mha``/``ff``, :91-119; lsm/topo concatenated whenever they are
+    passed, :232-241) is recognised by its keys."""
     E = "encoder."
+    clean = (E + "attention_layers.0.mha.in_proj_weight") in sd
+    akw = dict(mha="mha", ff=True, ffp="ff") if clean else {}
+    if clean:
+        has_lsm = lsm_cond is not None if has_lsm is None else has_lsm
+        has_topo = topo_cond is not None if has_topo is None else has_topo
     has_lsm = (E + "lsm") in sd if has_lsm is None else has_lsm
     has_topo = (E + "elevation") in sd if has_topo is None else has_topo
     # Encoder.forward :228-238 — concat order [x, lsm, topo, cond_img]
@@ -143,7 +150,7 @@ def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=N
     # :260-266 (no norm/activation between conv1 and attention)
     f = F.conv2d(x, sd[E + "conv1.weight"], None, 2, 3)
     f = f + _tproj(sd, E + "time_projection_layers.0", temb)[:, :, None, None]
-    f = image_self_attention(sd, E + "attention_layers.0", f, n_heads)
+    f = image_self_attention(sd, E + "attention_layers.0", f, n_heads, **akw)
     fm.append(f)
     # :269-282
     h = F.relu(_bn_eval(sd, E + "bn1", F.conv2d(f, sd[E + "conv2.weight"], None, 2, 3)))
@@ -151,7 +158,7 @@ def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=N
         for bi in range(2):
             h = _basic_block(sd, f"{E}layer{li}.{bi}.", h, 2 if (li > 1 and bi == 0) else 1)
         h = h + _tproj(sd, f"{E}time_projection_layers.{li}", temb)[:, :, None, None]
-        h = image_self_attention(sd, f"{E}attention_layers.{li}", h, n_heads)
+        h = image_self_attention(sd, f"{E}attention_layers.{li}", h, n_heads, **akw)
         fm.append(h)
         if taps is not None:
             taps[f"fmap{li + 1}"] = h
@@ -163,7 +170,7 @@ def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=N
     out = fm[4]
     for i in range(4):
         p = f"{D}residual_layers.{i}."
-        out = _decoder_block(sd, p, out, fm[3 - i], dtemb, n_heads)
+        out = _decoder_block(sd, p, out, fm[3 - i], dtemb, n_heads, akw)
         if taps is not None:
             taps[f"dec{i}"] = out
     # final_layer: no skip, no t, no attention, IN2 = Identity, act = Identity (:503-509, :535)
@@ -173,7 +180,7 @@ def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=N
     return F.conv2d(out, sd[p + "conv.weight"], sd[p + "conv.bias"], 1, 1)
 
 
-def _decoder_block(sd, p, fmap, prev, dtemb, n_heads):
+def _decoder_block(sd, p, fmap, prev, dtemb, n_heads, akw=None):
     """DecoderBlock.forward, modules_DANRA_conditional.py:425-460."""
     out = F.conv_transpose2d(fmap, sd[p + "transpose.weight"], sd[p + "transpose.bias"], stride=2)
     out = F.instance_norm(out, eps=1e-5)                            # affine=False, batch stats always
@@ -181,7 +188,7 @@ def _decoder_block(sd, p, fmap, prev, dtemb, n_heads):
     out = F.instance_norm(out, eps=1e-5)
     out = out + prev
     out = out + _tproj(sd, p + "time_projection_layer", dtemb)[:, :, None, None]
-    out = image_self_attention(sd, p + "attention", out, n_heads)
+    out = image_self_attention(sd, p + "attention", out, n_heads, **(akw or {}))
     return F.relu(out)
 
 

@@ -32,8 +32,20 @@ torch.set_num_threads(8)
 
 
 def build_ref_r(case, module_name="modules_DANRA_conditional"):
-    mod = __import__(module_name)
     H = case["hw"]
+    if case.get("clean"):
+        from DDPM_clean_application.src import unet as mod
+        enc = mod.Encoder(1, 256, cond_on_lsm=case["has_lsm"], cond_on_topo=case["has_topo"], cond_on_img=case["has_cond"],
+                          cond_img_dim=(1, H, H) if case["has_cond"] else None, num_classes=case["num_classes"],
+                          n_heads=case.get("n_heads", 4))
+        dec = mod.Decoder(512, 1, 256, 64, n_heads=case.get("n_heads", 4))
+        net = mod.DiffusionNet(enc, dec)
+        sd = synth.synth_state_dict_r(case["c_in"], 1, case["num_classes"], (H, H), case["has_lsm"], case["has_topo"],
+                                      seed=case["wseed"], randomize_bn=case["randomize_bn"], clean=True)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        return net
+    mod = __import__(module_name)
     lsm = torch.zeros(1, H, H) if case["has_lsm"] else None
     topo = torch.zeros(1, H, H) if case["has_topo"] else None
     enc = mod.Encoder(1, 256, lsm_tensor=lsm, topo_tensor=topo, cond_on_img=case["has_cond"],

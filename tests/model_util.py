@@ -7,6 +7,18 @@ from diffusionmodelscustom_b200 import synth
 
 def build_ours_r(case, device="cuda"):
     H = case["hw"]
+    if case.get("clean"):
+        from diffusionmodelscustom_b200 import unet as U
+        enc = U.Encoder(1, 256, cond_on_lsm=case["has_lsm"], cond_on_topo=case["has_topo"], cond_on_img=case["has_cond"],
+                        cond_img_dim=(1, H, H) if case["has_cond"] else None, num_classes=case["num_classes"],
+                        n_heads=case.get("n_heads", 4))
+        dec = U.Decoder(512, 1, 256, 64, n_heads=case.get("n_heads", 4))
+        net = U.DiffusionNet(enc, dec)
+        sd = synth.synth_state_dict_r(case["c_in"], 1, case["num_classes"], (H, H), case["has_lsm"], case["has_topo"],
+                                      seed=case["wseed"], randomize_bn=case["randomize_bn"], clean=True)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        return net.to(device), sd
     z = torch.zeros(1, H, H)
     enc = P.Encoder(1, 256, lsm_tensor=z if case["has_lsm"] else None, topo_tensor=z.clone() if case["has_topo"] else None,
                     cond_on_img=case["has_cond"], cond_img_dim=(1, H, H) if case["has_cond"] else None,

@@ -21,7 +21,8 @@ def rel_l2(a, b):
 def r_inputs(case, batch=None):
     B = batch or case["batch"]
     sd = synth.synth_state_dict_r(case["c_in"], 1, case["num_classes"], (case["hw"],) * 2, case["has_lsm"],
-                                  case["has_topo"], seed=case["wseed"], randomize_bn=case["randomize_bn"])
+                                  case["has_topo"], seed=case["wseed"], randomize_bn=case["randomize_bn"],
+                                  clean=case.get("clean", False))
     inp = synth.synth_inputs(B, case["hw"], seed=case["iseed"], has_lsm=case["has_lsm"], has_topo=case["has_topo"],
                              has_cond=case["has_cond"], num_classes=case["num_classes"])
     return sd, inp
