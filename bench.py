@@ -43,6 +43,12 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per launch (dram__bytes via ncu, cold-cache, averaged over the launches of the class) for the cfg2 step at batch 64:
+# profiles/r1_ncu_step_cfg2_b64_sections.txt.  Reported as roofline.traffic for that workload only.
+NCU_TRAFFIC_CFG2 = {"conv_tc": 3.57e6, "attn_tc": 15.76e6, "gemm_stream": None, "norm_fused": None, "layernorm": 5.6e6,
+                    "tail_conv": 33.6e6, "stem_conv": 17.9e6}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -274,6 +280,10 @@ def main():
                     "frac": ach / pk["hbm"], "traffic": None, "peak_source": pk["src"]}
         roof["avg_launch_ms"] = tk["ms"] / tk["launches"]
         roof["launches_per_step"] = tk["launches"]
+        roof["algorithmic_bytes_per_launch"] = tk["bytes"] / tk["launches"]
+        if args.workload == "cfg2" and batch == 64:
+            roof["traffic"] = NCU_TRAFFIC_CFG2.get(tname)
+            roof["traffic_source"] = "profiles/r1_ncu_step_cfg2_b64_sections.txt (ncu dram bytes per launch, cold cache)"
         whole = value * flops_per_sample_step * (T_STEPS - 1) / 1e12 / world
         cpu = None
         if not args.no_cpu_baseline:
