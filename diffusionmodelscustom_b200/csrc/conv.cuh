@@ -556,8 +556,9 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     p.splits = splits;
     pl.ws_floats = splits > 1 ? (size_t)tiles * splits * 128 * bn : 0;
     // deep pipelines for deep-K problems that leave SMs to spare anyway (the TMA round trip paces them)
-    pl.stages = (bn == 64) ? ((total_kb / splits >= 6 && tiles * splits <= num_sms) ? 8 : 4)
-                           : ((total_kb / splits >= 5 && tiles * splits <= num_sms) ? 6 : 3);
+    const int kb_cta = total_kb / splits;
+    const bool deep = tiles * splits <= num_sms && (splits == 1 ? kb_cta >= 6 : kb_cta >= 12);   // measured: 8-stage CTAs in
+    pl.stages = (bn == 64) ? (deep ? 8 : 4) : (deep ? 6 : 3);                                     // 8-CTA clusters schedule worse
     pl.grid = dim3(mtiles, p.Cout / bn, splits);
     const uint64_t C = p.Cin, W = p.Wi, H = p.Hi, B = p.B;
     if (p.stride == 1) {
