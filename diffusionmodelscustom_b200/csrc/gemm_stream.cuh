@@ -17,13 +17,18 @@
 
 namespace b2d {
 
-constexpr int GS_THREADS = 192;
+constexpr int GS_EPI_WARPS = 16;
+constexpr int GS_EPI_THREADS = GS_EPI_WARPS * 32;
+constexpr int GS_THREADS = 64 + GS_EPI_THREADS;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..17: epilogue
 
 template <int KB>
-__host__ __device__ constexpr int gs_stages() { return KB == 1 ? 6 : 2; }
+__host__ __device__ constexpr int gs_stages() { return KB == 1 ? 4 : 2; }
+template <int KB>
+__host__ __device__ constexpr int gs_out_bufs() { return KB == 1 ? 4 : 2; }   // output staging tiles (TMA stores in flight)
 template <int KB>
 __host__ __device__ constexpr int gs_smem_bytes() {
-    return gs_stages<KB>() * KB * CONV_A_BYTES + KB * 256 * 128 + 4 * CONV_A_BYTES /*store staging + residual ring*/ + 1024 + 256;
+    return gs_stages<KB>() * KB * CONV_A_BYTES + KB * 256 * 128 + (gs_out_bufs<KB>() + 2) * CONV_A_BYTES /*store staging + residual ring*/ +
+           1024 + 256;
 }
 
 template <int KB>
@@ -37,21 +42,24 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gs_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                                        // STAGES x KB x 16 KB
     uint8_t* sB = smem + STAGES * KB * CONV_A_BYTES;           // KB x NB x 128 B (resident weights)
-    uint8_t* sO = sB + KB * 256 * 128;                         // 2 x 16 KB output staging (128 rows x 64 ch, 128B swizzle)
-    uint8_t* sR = sO + 2 * CONV_A_BYTES;                       // 2 x 16 KB residual blocks, TMA-prefetched by the producer
+    constexpr int OB = gs_out_bufs<KB>();
+    constexpr int OBP = OB / 2;                                // staging tiles per epilogue pair
+    uint8_t* sO = sB + KB * 256 * 128;                         // OB x 16 KB output staging (128 rows x 64 ch, 128B swizzle)
+    uint8_t* sR = sO + OB * CONV_A_BYTES;                      // 2 x 16 KB residual blocks, TMA-prefetched by the producer
     uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 2 * CONV_A_BYTES);
     uint64_t* a_full = bars;                 // [STAGES]
     uint64_t* a_empty = bars + STAGES;       // [STAGES]
     uint64_t* t_full = bars + 2 * STAGES;    // [2] accumulator ready
-    uint64_t* t_empty = t_full + 2;          // [2] accumulator drained (4 epilogue warps)
+    uint64_t* t_empty = t_full + 2;          // [2] accumulator drained (epilogue warps)
     uint64_t* b_full = t_empty + 2;
     uint64_t* r_full = b_full + 1;           // [2]
-    uint64_t* r_empty = r_full + 2;          // [2] (4 epilogue warps)
+    uint64_t* r_empty = r_full + 2;          // [2] (epilogue warps)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nblk = blockIdx.y;
     const int num_tiles = (M + 127) / 128;
+    __shared__ __align__(16) float2 s_stat[2 * 512];          // per-group partial (sum, sum of squares) of the LN statistics, double-buffered
     __shared__ __align__(16) float s_bias[256], s_c1[256];   // bias / LN column sums of this CTA's N block (persistent => loaded once)
     for (int i = threadIdx.x; i < NB; i += GS_THREADS) {
         const int col = nblk * NB + i;
@@ -69,16 +77,16 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
         if (lane == 0) {
             for (int i = 0; i < STAGES; ++i) {
                 mbar_init(&a_full[i], 1);
-                mbar_init(&a_empty[i], p.ln_c1 ? 5 : 1);     // + the four epilogue warps when they read A for the LN statistics
+                mbar_init(&a_empty[i], p.ln_c1 ? 1 + GS_EPI_WARPS : 1);   // + the epilogue warps when they read A for the LN statistics
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&t_full[i], 1);
-                mbar_init(&t_empty[i], 4);
+                mbar_init(&t_empty[i], GS_EPI_WARPS);
             }
             mbar_init(b_full, 1);
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&r_full[i], 1);
-                mbar_init(&r_empty[i], 4);
+                mbar_init(&r_empty[i], GS_EPI_WARPS / 2);
             }
             fence_mbar_init();
         }
@@ -138,85 +146,103 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
         }
         __syncwarp();
     } else {
+        // 16 epilogue warps = 4 groups of 128 threads (one TMEM lane quarter per warp, warp % 4).  Groups 2p and 2p+1 form
+        // pair p: the pair owns every second 64-column output block (running block counter & 1), its two groups take the
+        // low / high 32 columns of it.  One warp per scheduler cannot hide the tcgen05.ld -> FMA -> pack -> st.shared
+        // dependency chain (measured 5 clk per issued instruction); four per scheduler can.
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2, pair = grp >> 1, half = grp & 1;
         const int row = q * 32 + lane;
         const int HW = p.Ho * p.Wo;
         const int sw = row & 7;
-        int it = 0, blk = 0;                                   // blk: running 64-column block counter (staging buffer = blk & 1)
+        const bool elected = (warp - 2) == pair * 8 && lane == 0;      // issues this pair's TMA stores
+        const int bar_id = 1 + pair;
+        int it = 0, blk = 0;                                   // blk: running 64-column block counter
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const int m0 = t * 128;
             const int m = m0 + row;
             const int mr = m < M ? m : M - 1;                 // rows past the end are clipped by the TMA store
             const int n = mr / HW;
-            float ln_mu = 0.f, ln_rstd = 1.f;
+            float ln_a = 1.f, ln_b = 0.f;                     // out = ln_a * acc + (ln_b * c1 + bias)
             if (p.ln_c1 != nullptr) {
                 const int st = it % STAGES;
                 mbar_wait(&a_full[st], (it / STAGES) & 1);
                 float s1 = 0.f, s2 = 0.f;
+                // each group sums a quarter of the row (swizzle order: conflict-free, and a sum does not care)
+                constexpr int PER = KB * 2;
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint4* arow = reinterpret_cast<const uint4*>(sA + (st * KB + kb) * CONV_A_BYTES + row * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const uint4 a4 = arow[j ^ sw];          // swizzle order: conflict-free, and a sum does not care
-                        float2 tt;
-                        tt = unpack_h2(a4.x); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
-                        tt = unpack_h2(a4.y); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
-                        tt = unpack_h2(a4.z); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
-                        tt = unpack_h2(a4.w); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
-                    }
+                for (int jj = 0; jj < PER; ++jj) {
+                    const int j = grp * PER + jj;               // 16-byte chunk index within the K = KB*64 row
+                    const uint4* arow = reinterpret_cast<const uint4*>(sA + (st * KB + (j >> 3)) * CONV_A_BYTES + row * 128);
+                    const uint4 a4 = arow[(j & 7) ^ sw];
+                    float2 tt;
+                    tt = unpack_h2(a4.x); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                    tt = unpack_h2(a4.y); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                    tt = unpack_h2(a4.z); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                    tt = unpack_h2(a4.w); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_empty[st]);
+                float2* sst = s_stat + (it & 1) * 512;
+                sst[grp * 128 + row] = make_float2(s1, s2);
+                named_bar_sync(3, GS_EPI_THREADS);
+                s1 = 0.f; s2 = 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {                   // fixed order: every group derives bit-identical statistics
+                    const float2 v2 = sst[g * 128 + row];
+                    s1 += v2.x; s2 += v2.y;
+                }
                 const float invk = 1.0f / (float)(KB * 64);
-                ln_mu = s1 * invk;
-                ln_rstd = rsqrtf(fmaxf(s2 * invk - ln_mu * ln_mu, 0.f) + 1e-5f);
+                const float mu = s1 * invk;
+                ln_a = rsqrtf(fmaxf(s2 * invk - mu * mu, 0.f) + 1e-5f);
+                ln_b = -ln_a * mu;
             }
             mbar_wait(&t_full[acc], (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
             for (int jb = 0; jb < NB / 64; ++jb, ++blk) {
-                uint8_t* stg = sO + (blk & 1) * CONV_A_BYTES;
+                if ((blk & 1) != pair) continue;
+                uint8_t* stg = sO + (pair * OBP + ((blk >> 1) % OBP)) * CONV_A_BYTES;
                 uint4* srow = reinterpret_cast<uint4*>(stg + row * 128);
-                if (threadIdx.x == 64) tma_store_wait_read_le1();   // the store that used this buffer two blocks ago has read it
-                named_bar_sync(1, 128);
+                if (elected) tma_store_wait_read_n<OBP - 1>();   // the store that used this buffer OBP blocks ago has read it
+                named_bar_sync(bar_id, 256);
                 const int col = nblk * NB + jb * 64;           // GEMM column of this block
                 int cbase = col, ab = 0;
                 if (p.convt) {
                     ab = col / p.CoutT;
                     cbase = col - ab * p.CoutT;
                 }
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
+                {
                     uint32_t v[32];
                     tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + jb * 64 + half * 32), v);
                     tmem_ld_wait();
                     const int c0 = cbase + half * 32;
                     float f[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     const int lc = jb * 64 + half * 32;             // column within this CTA's N block
                     if (p.ln_c1) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 c4 = *reinterpret_cast<const float4*>(&s_c1[lc + j]);
-                            f[j] = ln_rstd * (f[j] - ln_mu * c4.x);
-                            f[j + 1] = ln_rstd * (f[j + 1] - ln_mu * c4.y);
-                            f[j + 2] = ln_rstd * (f[j + 2] - ln_mu * c4.z);
-                            f[j + 3] = ln_rstd * (f[j + 3] - ln_mu * c4.w);
+                            const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[lc + j]);
+                            f[j] = fmaf(ln_a, __uint_as_float(v[j]), fmaf(ln_b, c4.x, b4.x));
+                            f[j + 1] = fmaf(ln_a, __uint_as_float(v[j + 1]), fmaf(ln_b, c4.y, b4.y));
+                            f[j + 2] = fmaf(ln_a, __uint_as_float(v[j + 2]), fmaf(ln_b, c4.z, b4.z));
+                            f[j + 3] = fmaf(ln_a, __uint_as_float(v[j + 3]), fmaf(ln_b, c4.w, b4.w));
                         }
-                    }
-                    {
+                    } else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[lc + j]);
-                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                            f[j] = __uint_as_float(v[j]) + b4.x;
+                            f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+                            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
+                            f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
                         }
                     }
-                    if (p.residual) {   // non-convT only (checked on the host): residual block TMA-prefetched into sR
-                        if (half == 0) mbar_wait(&r_full[blk & 1], (blk >> 1) & 1);
-                        const uint4* rrow = reinterpret_cast<const uint4*>(sR + (blk & 1) * CONV_A_BYTES + row * 128);
+                    if (p.residual) {   // non-convT only (checked on the host): residual block TMA-prefetched into sR[pair]
+                        mbar_wait(&r_full[pair], (blk >> 1) & 1);
+                        const uint4* rrow = reinterpret_cast<const uint4*>(sR + pair * CONV_A_BYTES + row * 128);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const uint4 r4 = rrow[(half * 4 + j) ^ sw];
@@ -226,6 +252,8 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                             tt = unpack_h2(r4.z); f[j * 8 + 4] += tt.x; f[j * 8 + 5] += tt.y;
                             tt = unpack_h2(r4.w); f[j * 8 + 6] += tt.x; f[j * 8 + 7] += tt.y;
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&r_empty[pair]);
                     }
                     if (p.act) {
 #pragma unroll
@@ -249,13 +277,9 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                         srow[(half * 4 + j) ^ sw] = o;
                     }
                 }
-                if (p.residual) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&r_empty[blk & 1]);
-                }
                 fence_proxy_async();
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 64) {
+                named_bar_sync(bar_id, 256);
+                if (elected) {
                     if (p.convt) {
                         const int n0 = m0 / HW, rem = m0 - n0 * HW;
                         tma_store_5d(&tmO, stg, (ab & 1) * p.CoutT + cbase, rem % p.Wo, ab >> 1, rem / p.Wo, n0);
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
         }
-        if (threadIdx.x == 64) tma_store_wait_all();
+        if (elected) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
