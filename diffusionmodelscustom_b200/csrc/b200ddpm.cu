@@ -114,6 +114,13 @@ struct Handle {
     bool is_kid = false;
     cudaEvent_t ev_fork = nullptr;
     std::vector<cudaEvent_t> ev_join;
+    // Time-embedding pipelining inside the reverse loop: d_temb depends on the step index only, so the projections for
+    // step i-1 are launched on a side stream as soon as step i's last reader of d_temb has been enqueued, and overlap the
+    // final layer + posterior update (a concurrent branch of the captured step graph).
+    int temb_free_op = -1;   // index of the first step op after the last reader of d_temb (set by the program builders)
+    int temb_t_off = 0;      // added to d_t by the next temb launch (-1 on the side branch)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
     struct Tap { const f16* p; int C, hw; };
     std::map<std::string, Tap> taps;  // named activations (NHWC f16) readable through b2d_debug_read
 
@@ -146,6 +153,9 @@ struct Handle {
         free_program();
         for (void* p : allocs) cudaFree(p);
         if (own_stream) cudaStreamDestroy(own_stream);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (ev_side_fork) cudaEventDestroy(ev_side_fork);
+        if (ev_side_join) cudaEventDestroy(ev_side_join);
     }
 };
 
@@ -605,7 +615,7 @@ static int build_program_r(Handle* h, int B) {
         ops.push_back([=](cudaStream_t st) {
             dim3 grid((TS + TEMB_OC - 1) / TEMB_OC, (B + TEMB_SB - 1) / TEMB_SB);
             B2D_CUDA(launch_k(temb_project_kernel, dim3(grid), dim3(256), 0, st, hh->d_t, hh->has_y ? hh->d_y : nullptr, label, ei, dd, tw, tb, temb, 1024,
-                                                      TS, B));
+                                                      TS, B, hh->temb_t_off));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -693,6 +703,7 @@ static int build_program_r(Handle* h, int B) {
         h->taps["dec" + std::to_string(i)] = {dout, co, hout};
         dcur = dout;
     }
+    h->temb_free_op = (int)ops.v.size();   // nothing below reads d_temb
     // ---- final_layer: ConvT -> IN -> Conv3x3(64->c_out), no skip/time/attention/activation (:503-509, :535)
     {
         f16* up = bd.act((size_t)B * H * H * 64);
@@ -861,10 +872,30 @@ static int ensure_program(Handle* h, int B) {
     return rc;
 }
 
-static int run_step_ops(Handle* h, cudaStream_t st) {
+// pipelined = inside the reverse loop: op 0 (time embeddings) of this step was produced by the previous step's side branch
+// (or by the loop prologue), and the embeddings of the NEXT step are launched on the side stream at temb_free_op.  The
+// caller joins the side branch (join_temb_side) before it advances the step counter.
+static int run_step_ops(Handle* h, cudaStream_t st, bool pipelined = false) {
     static const bool dbg = getenv("B2D_DEBUG_SYNC") != nullptr;
+    static const bool no_pipe = getenv("B2D_NO_TEMB_PIPE") != nullptr;
+    const bool pipe = pipelined && !no_pipe && h->temb_free_op > 0;
+    if (pipe && !h->side_stream) {
+        B2D_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        B2D_CUDA(cudaEventCreateWithFlags(&h->ev_side_fork, cudaEventDisableTiming));
+        B2D_CUDA(cudaEventCreateWithFlags(&h->ev_side_join, cudaEventDisableTiming));
+    }
     int idx = 0;
     for (auto& op : h->step_ops) {
+        if (pipe && idx == 0) { ++idx; continue; }
+        if (pipe && idx == h->temb_free_op) {
+            B2D_CUDA(cudaEventRecord(h->ev_side_fork, st));
+            B2D_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_side_fork, 0));
+            h->temb_t_off = -1;
+            const int rc = h->step_ops[0](h->side_stream);
+            h->temb_t_off = 0;
+            if (rc) return rc;
+            B2D_CUDA(cudaEventRecord(h->ev_side_join, h->side_stream));
+        }
         B2D_TRY(op(st));
         if (dbg) {
             cudaError_t e = cudaStreamSynchronize(st);
@@ -873,6 +904,15 @@ static int run_step_ops(Handle* h, cudaStream_t st) {
         }
         ++idx;
     }
+    return 0;
+}
+
+static bool temb_pipelined(const Handle* h) {
+    static const bool no_pipe = getenv("B2D_NO_TEMB_PIPE") != nullptr;
+    return !no_pipe && h->temb_free_op > 0;
+}
+static int join_temb_side(Handle* h, cudaStream_t st) {
+    if (temb_pipelined(h)) B2D_CUDA(cudaStreamWaitEvent(st, h->ev_side_join, 0));
     return 0;
 }
 
@@ -1082,6 +1122,7 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
         for (auto& p : parts) {
             B2D_CUDA(launch_k(fill_int_kernel, dim3((p.Bi + 255) / 256), dim3(256), 0, st, p.ph->d_t, T - 1, p.Bi));
             B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, p.ph->d_step, T - 1, 1));
+            if (temb_pipelined(p.ph)) B2D_TRY(p.ph->step_ops[0](st));   // embeddings of the first step; later ones come from the side branch
         }
         int64_t launches = 0;
         for (int i = T - 1; i >= 1; --i) {
@@ -1089,13 +1130,14 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
                 float* xs = x_inout + (size_t)p.b0 * per_sample;
                 p.ph->cur_x = xs;
                 p.ph->cur_eps = p.ph->d_eps;
-                B2D_TRY(run_step_ops(p.ph, st));
+                B2D_TRY(run_step_ops(p.ph, st, true));
                 const size_t ni = per_sample * p.Bi;
                 const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
                 B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, xs, p.ph->d_eps,
                                   noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
                                   p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
                                   noise_scale, n));
+                B2D_TRY(join_temb_side(p.ph, st));
                 B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, st, p.ph->d_step, p.ph->d_t, p.Bi));
                 launches += (int64_t)p.ph->step_ops.size() + 2;
             }
@@ -1121,13 +1163,14 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
                 float* xs = x_inout + (size_t)p.b0 * per_sample;
                 p.ph->cur_x = xs;
                 p.ph->cur_eps = p.ph->d_eps;
-                B2D_TRY(run_step_ops(p.ph, si));
+                B2D_TRY(run_step_ops(p.ph, si, true));
                 const size_t ni = per_sample * p.Bi;
                 const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
                 B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, si, xs, p.ph->d_eps,
                                   noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
                                   p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
                                   noise_scale, n));
+                B2D_TRY(join_temb_side(p.ph, si));
                 B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, si, p.ph->d_step, p.ph->d_t, p.Bi));
                 if (i > 0) {
                     B2D_CUDA(cudaEventRecord(h->ev_join[i], si));
@@ -1156,6 +1199,7 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
     for (auto& p : parts) {
         B2D_CUDA(launch_k(fill_int_kernel, dim3((p.Bi + 255) / 256), dim3(256), 0, st, p.ph->d_t, T - 1, p.Bi));
         B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, p.ph->d_step, T - 1, 1));
+        if (temb_pipelined(p.ph)) B2D_TRY(p.ph->step_ops[0](st));   // embeddings of the first step; later ones come from the side branch
     }
     for (int i = T - 1; i >= 1; --i) B2D_CUDA(cudaGraphLaunch(h->graph_exec, st));
     h->last_launches = (int64_t)h->graph_nodes * (T - 1) + 2 * (int64_t)parts.size();

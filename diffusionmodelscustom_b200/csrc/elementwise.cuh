@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
                                                            const float* __restrict__ W,          // [n_out][256]
                                                            const float* __restrict__ bias,       // [n_out]
                                                            float* __restrict__ out,              // [B][n_out]
-                                                           int n_enc, int n_out, int B) {
+                                                           int n_enc, int n_out, int B, int t_off) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float se[TEMB_SB][TEMB_DIM], sd[TEMB_SB][TEMB_DIM];
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
 #pragma unroll
         for (int sidx = 0; sidx < TEMB_SB; ++sidx) {
             const int b = min(b0 + sidx, B - 1);
-            const float tf = (float)t[b];
+            const float tf = (float)(t[b] + t_off);   // t_off = -1: embeddings of the NEXT reverse step
             if (need_enc) {
                 const float a = tf * inv;
                 float e = (k < 128) ? sinf(a) : cosf(a);
@@ -329,11 +329,20 @@ __global__ void __launch_bounds__(256, 2) tail_conv_kernel(const f16* __restrict
     cp_async_wait<0>();
     __syncthreads();
     for (int oc = 0; oc < c_out; ++oc) {
-        float wr[9][8];
+        // (v - mean) * rstd * w  ==  v * (rstd * w) - mean * rstd * w: the normalisation is folded into the 72 weights of this
+        // thread's channels, and the mean term becomes one constant per filter tap, subtracted only for in-image taps
+        // (zero padding applies to the NORMALISED tensor; out-of-image pixels are zero-filled in the tile and add nothing).
+        float wr[9][8], mt[9];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap)
+        for (int tap = 0; tap < 9; ++tap) {
+            float m = 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) wr[tap][c] = __ldg(w + ((size_t)oc * 64 + cgp * 8 + c) * 9 + tap);
+            for (int c = 0; c < 8; ++c) {
+                wr[tap][c] = __ldg(w + ((size_t)oc * 64 + cgp * 8 + c) * 9 + tap) * rstd[c];
+                m = fmaf(wr[tap][c], mean[c], m);
+            }
+            mt[tap] = m;
+        }
         float acc[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(256, 2) tail_conv_kernel(const f16* __restrict
 #pragma unroll
             for (int sx = 0; sx < 3; ++sx) {
                 const int wi = wcol + sx - 1;
-                const bool ok = rok && wi >= 0 && wi < W;   // zero padding applies to the NORMALISED tensor
+                const bool ok = rok && wi >= 0 && wi < W;
                 const uint4 raw = *reinterpret_cast<const uint4*>(tile + ((size_t)(ir * 34 + lcol + sx)) * 64 + cgp * 8);
                 float v[8];
                 float2 t2;
@@ -353,12 +362,10 @@ __global__ void __launch_bounds__(256, 2) tail_conv_kernel(const f16* __restrict
                 t2 = unpack_h2(raw.z); v[4] = t2.x; v[5] = t2.y;
                 t2 = unpack_h2(raw.w); v[6] = t2.x; v[7] = t2.y;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = ok ? (v[c] - mean[c]) * rstd[c] : 0.f;
-#pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const int orow = ir - r;  // output row (within the strip) that sees this input row through filter row r
                     if (orow < 0 || orow >= 8) continue;
-                    float a = acc[orow];
+                    float a = acc[orow] - (ok ? mt[r * 3 + sx] : 0.f);
 #pragma unroll
                     for (int c = 0; c < 8; ++c) a = fmaf(v[c], wr[r * 3 + sx][c], a);
                     acc[orow] = a;

@@ -484,7 +484,7 @@ static int build_program_d(Handle* h, int B) {
         ops.meta("temb", "temb_project", 2.0 * B * TS * 256, 4.0 * TS * 256);
         ops.push_back([=](cudaStream_t st) {
             dim3 grid((TS + TEMB_OC - 1) / TEMB_OC, (B + TEMB_SB - 1) / TEMB_SB);
-            B2D_CUDA(launch_k(temb_project_kernel, grid, dim3(256), 0, st, hh->d_t, nullptr, nullptr, ei, dd, tw, tb, temb, TS, TS, B));
+            B2D_CUDA(launch_k(temb_project_kernel, grid, dim3(256), 0, st, hh->d_t, nullptr, nullptr, ei, dd, tw, tb, temb, TS, TS, B, hh->temb_t_off));
             return 0;
         });
     }
@@ -554,7 +554,9 @@ static int build_program_d(Handle* h, int B) {
     h->taps["bot"] = {x4, 256, H / 8};
     f16* u1 = sa(up(x4, H / 8, 256, x3, 256, 128, "up1", D_TEMB_OFF[3]), H / 4, 128, "sa4");
     f16* u2 = sa(up(u1, H / 4, 128, x2, 128, 64, "up2", D_TEMB_OFF[4]), H / 2, 64, "sa5");
-    f16* u3 = sa(up(u2, H / 2, 64, x1, 64, 64, "up3", D_TEMB_OFF[5]), H, 64, "sa6");
+    f16* u3_pre = up(u2, H / 2, 64, x1, 64, 64, "up3", D_TEMB_OFF[5]);
+    h->temb_free_op = (int)ops.v.size();   // nothing below reads d_temb
+    f16* u3 = sa(u3_pre, H, 64, "sa6");
     h->taps["u1"] = {u1, 128, H / 4};
     h->taps["u2"] = {u2, 64, H / 2};
     h->taps["u3"] = {u3, 64, H};

@@ -175,8 +175,11 @@ inline int norm_fused_cluster(int rows) {
 
 template <int MODE>
 inline int norm_fused_launch(const NormParams& p, int B, int groups, cudaStream_t st) {
-    const int cs = norm_fused_cluster(p.rows);
+    int cs = norm_fused_cluster(p.rows);
     B2D_CHECK(cs > 0, "normalisation slab does not fit a cluster");
+    // small batches: spread each slab over a wider cluster until the grid covers the SMs about twice (the kernel is a
+    // load -> reduce -> cluster barrier -> store chain per CTA, so its duration follows rows per CTA, not total bytes)
+    while (cs < 8 && cs * groups * B < 2 * 148 && p.rows / (2 * cs) >= 32) cs *= 2;
     NormParams q = p;
     q.rows_per_cta = (p.rows + cs - 1) / cs;
     cudaLaunchConfig_t cfg{};
