@@ -45,6 +45,8 @@ struct Op {
     double flops = 0;   // algorithmic FLOPs of this launch (2*M*N*K; attention 4*L^2*C per sample)
     double bytes = 0;   // algorithmic HBM bytes of this launch (activations read + written, weights once)
     OpFn fn;
+    bool side = false;  // independent of the next op(s): launched on the handle's side stream (a concurrent graph branch)
+    bool join = false;  // first op that consumes the side branch's result: waits for it
     int operator()(cudaStream_t st) const { return fn(st); }
 };
 struct OpList {
@@ -121,6 +123,7 @@ struct Handle {
     int temb_t_off = 0;      // added to d_t by the next temb launch (-1 on the side branch)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
+    cudaEvent_t ev_br_fork = nullptr, ev_br_join = nullptr;   // Op::side / Op::join branches
     struct Tap { const f16* p; int C, hw; };
     std::map<std::string, Tap> taps;  // named activations (NHWC f16) readable through b2d_debug_read
 
@@ -156,6 +159,8 @@ struct Handle {
         if (side_stream) cudaStreamDestroy(side_stream);
         if (ev_side_fork) cudaEventDestroy(ev_side_fork);
         if (ev_side_join) cudaEventDestroy(ev_side_join);
+        if (ev_br_fork) cudaEventDestroy(ev_br_fork);
+        if (ev_br_join) cudaEventDestroy(ev_br_join);
     }
 };
 
@@ -659,12 +664,14 @@ static int build_program_r(Handle* h, int B) {
         f16* pre = bd.act(n_out);
         const f16* identity = cur;
         const int stride = (li > 1) ? 2 : 1;
-        bd.conv(cur, hin, hin, cin, t1, cout, 3, stride, 1, false, r0 + ".c1", nullptr, nullptr, 0, 1);
-        if (li > 1) {
+        if (li > 1) {   // the 1x1/s2 downsample only depends on the block input: a side branch next to c1
             f16* ds = bd.act(n_out);
+            ops.pending.side = true;
             bd.conv(cur, hin, hin, cin, ds, cout, 1, 2, 0, false, r0 + ".ds", nullptr, nullptr, 0, 0);
             identity = ds;
         }
+        bd.conv(cur, hin, hin, cin, t1, cout, 3, stride, 1, false, r0 + ".c1", nullptr, nullptr, 0, 1);
+        ops.pending.join = (li > 1);
         bd.conv(t1, hout, hout, cout, b0, cout, 3, 1, 1, false, r0 + ".c2", identity, nullptr, 0, 1);
         bd.conv(b0, hout, hout, cout, t1, cout, 3, 1, 1, false, r1 + ".c1", nullptr, nullptr, 0, 1);
         // last conv of the stage: + identity, ReLU, then + time projection (fmap = layer(x) + t_emb, :276-280)
@@ -878,15 +885,32 @@ static int ensure_program(Handle* h, int B) {
 static int run_step_ops(Handle* h, cudaStream_t st, bool pipelined = false) {
     static const bool dbg = getenv("B2D_DEBUG_SYNC") != nullptr;
     static const bool no_pipe = getenv("B2D_NO_TEMB_PIPE") != nullptr;
+    static const bool no_branch = getenv("B2D_NO_BRANCH") != nullptr;
     const bool pipe = pipelined && !no_pipe && h->temb_free_op > 0;
-    if (pipe && !h->side_stream) {
+    if (!h->side_stream) {
         B2D_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
         B2D_CUDA(cudaEventCreateWithFlags(&h->ev_side_fork, cudaEventDisableTiming));
         B2D_CUDA(cudaEventCreateWithFlags(&h->ev_side_join, cudaEventDisableTiming));
+        B2D_CUDA(cudaEventCreateWithFlags(&h->ev_br_fork, cudaEventDisableTiming));
+        B2D_CUDA(cudaEventCreateWithFlags(&h->ev_br_join, cudaEventDisableTiming));
     }
     int idx = 0;
+    bool branch_open = false;
     for (auto& op : h->step_ops) {
         if (pipe && idx == 0) { ++idx; continue; }
+        if (op.side && !no_branch && !dbg) {
+            B2D_CUDA(cudaEventRecord(h->ev_br_fork, st));
+            B2D_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_br_fork, 0));
+            B2D_TRY(op(h->side_stream));
+            B2D_CUDA(cudaEventRecord(h->ev_br_join, h->side_stream));
+            branch_open = true;
+            ++idx;
+            continue;
+        }
+        if (op.join && branch_open) {
+            B2D_CUDA(cudaStreamWaitEvent(st, h->ev_br_join, 0));
+            branch_open = false;
+        }
         if (pipe && idx == h->temb_free_op) {
             B2D_CUDA(cudaEventRecord(h->ev_side_fork, st));
             B2D_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_side_fork, 0));

@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                     p.gn_partial[t + 1] = (s_bias[1] + s_bias[3]) + (s_bias[5] + s_bias[7]);
                 }
             }
-            if (threadIdx.x == 64) tma_store_wait_all();           // smem must outlive the bulk reads; writes done before exit
+            if (threadIdx.x == 64) tma_store_wait_read();          // smem must outlive the bulk reads; the writes complete with the grid
         }
     }
     if (p.splits > 1) {

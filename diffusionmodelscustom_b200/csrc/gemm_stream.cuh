@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
         }
-        if (elected) tma_store_wait_all();
+        if (elected) tma_store_wait_read();   // smem must outlive the bulk reads; the writes complete with the grid
     }
     tc_fence_before();
     __syncthreads();
