@@ -635,11 +635,17 @@ static int build_program_r(Handle* h, int B) {
         ops.meta("conv1", "stem_conv", 2.0 * B * ho * ho * 64 * 64 * chr,
                  (double)B * (4.0 * chr * Hh * Hh + ho * ho * 64 * (2 + 4)));
         ops.push_back([=](cudaStream_t st) {
-            dim3 grid(ho / 16, ho / 16, B);
             const bool have_cond = (cin_total > chr);
-            B2D_CUDA(launch_k(stem_conv_kernel<8, 2>, dim3(grid), dim3(256), 0, st, hh->cur_x, chr, Hh, Hh, sw, cin_total, 0,
-                                                         have_cond ? hh->d_cond_pre : nullptr, temb + TEMB_ENC_OFF[0], TS,
-                                                         f1_pre, nullptr, ho, ho, 3));
+            const float* addp = have_cond ? hh->d_cond_pre : nullptr;
+            if (ho % 16 == 0) {   // tensor-core stem (hi/lo split operands, fp32-equivalent)
+                dim3 grid(ho / 16, ho / 16, B);
+                B2D_CUDA(launch_k(stem_mma_kernel, dim3(grid), dim3(256), STEM_MMA_SMEM, st, hh->cur_x, chr, Hh, Hh, sw, addp,
+                                  temb + TEMB_ENC_OFF[0], TS, f1_pre, ho, ho));
+            } else {
+                dim3 grid((ho + 15) / 16, (ho + 15) / 16, B);
+                B2D_CUDA(launch_k(stem_conv_kernel<8, 2>, dim3(grid), dim3(256), 0, st, hh->cur_x, chr, Hh, Hh, sw, cin_total, 0, addp,
+                                  temb + TEMB_ENC_OFF[0], TS, f1_pre, nullptr, ho, ho, 3));
+            }
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -765,6 +771,7 @@ static int init_uniform_carveout() {
     B2D_TRY(set_carveout(attn_tc_kernel));
     B2D_TRY(set_carveout(temb_project_kernel));
     B2D_TRY(set_carveout(stem_conv_kernel<8, 2>));
+    B2D_CUDA(cudaFuncSetAttribute(stem_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_MMA_SMEM));
     B2D_TRY(set_carveout(stem_conv_kernel<3, 1>));
     B2D_TRY(set_carveout(plane_stats_kernel));
     B2D_TRY(set_carveout(instnorm_apply_kernel));

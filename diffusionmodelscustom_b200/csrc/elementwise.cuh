@@ -189,6 +189,127 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
     }
 }
 
+// Tensor-core version of the per-step 8x8 / stride 2 / pad 3 stem (Encoder.conv1 on the diffusion state), used when the
+// output extent is a multiple of 16.  The fp32 state is NOT rounded: x and w are split into fp16 (hi, lo) pairs and the
+// product is formed as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation (mma.sync m16n8k16; error ~2^-22).
+// CTA = 16x16 output pixels x 64 channels, 8 warps; warp = 2 output rows (two m16 tiles) x all 64 channels.
+// GEMM view per input channel: M = pixel, K = 64 taps (k-tile = two filter rows), N = 64.  The A fragments are plain
+// 32-bit shared-memory loads from the (38 x 38) input tile: tap (ky, kx) of output pixel (oy, ox) is tile[2oy+ky][2ox+kx],
+// and a fragment register holds two consecutive kx.  Epilogue: + precomputed conditioning part (fp32) + time projection,
+// fp16 rows staged per warp in swizzled shared memory and written as full 128-byte lines.
+constexpr int STEM_IT = 38, STEM_XP = 40, STEM_WP = 72;
+constexpr int STEM_MMA_SMEM = 2 * STEM_IT * STEM_XP * 2 + 2 * 64 * STEM_WP * 2 + 8 * 4096 + 64 * 4;
+__global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restrict__ in, int Cx, int Hi, int Wi,
+                                                          const float* __restrict__ w,    // packed [Cin_total][64 taps][64]
+                                                          const float* __restrict__ add,  // [B,Ho,Wo,64] fp32 or null
+                                                          const float* __restrict__ vec, int vec_stride,
+                                                          f16* __restrict__ out, int Ho, int Wo) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) uint8_t stem_smem[];
+    f16* s_xh = reinterpret_cast<f16*>(stem_smem);
+    f16* s_xl = s_xh + STEM_IT * STEM_XP;
+    f16* s_wh = s_xl + STEM_IT * STEM_XP;
+    f16* s_wl = s_wh + 64 * STEM_WP;
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_wl + 64 * STEM_WP);
+    float* s_vec = reinterpret_cast<float*>(s_stage + 8 * 1024);
+    const int b = blockIdx.z;
+    const int ho0 = blockIdx.y * 16, wo0 = blockIdx.x * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tg = lane & 3;
+    if (threadIdx.x < 64) s_vec[threadIdx.x] = vec ? vec[(size_t)b * vec_stride + threadIdx.x] : 0.f;
+    float acc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    for (int c = 0; c < Cx; ++c) {
+        __syncthreads();
+        const float* ip = in + ((size_t)b * Cx + c) * Hi * Wi;
+        for (int i = threadIdx.x; i < STEM_IT * STEM_IT; i += 256) {
+            const int iy = i / STEM_IT, ix = i - iy * STEM_IT;
+            const int gy = ho0 * 2 - 3 + iy, gx = wo0 * 2 - 3 + ix;
+            const float v = (gy >= 0 && gy < Hi && gx >= 0 && gx < Wi) ? ip[(size_t)gy * Wi + gx] : 0.f;
+            const f16 hi = __float2half_rn(v);
+            s_xh[iy * STEM_XP + ix] = hi;
+            s_xl[iy * STEM_XP + ix] = __float2half_rn(v - __half2float(hi));
+        }
+        const float* wsrc = w + (size_t)c * 4096;
+        for (int i = threadIdx.x; i < 4096; i += 256) {
+            const int tap = i >> 6, n = i & 63;
+            const float v = __ldg(wsrc + i);
+            const f16 hi = __float2half_rn(v);
+            s_wh[n * STEM_WP + tap] = hi;
+            s_wl[n * STEM_WP + tap] = __float2half_rn(v - __half2float(hi));
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int kt = 0; kt < 4; ++kt) {
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const int base = (2 * (2 * warp + mt) + 2 * kt) * STEM_XP + 2 * g + 2 * tg;
+                ah[mt][0] = *reinterpret_cast<const uint32_t*>(s_xh + base);
+                ah[mt][1] = *reinterpret_cast<const uint32_t*>(s_xh + base + 16);
+                ah[mt][2] = *reinterpret_cast<const uint32_t*>(s_xh + base + STEM_XP);
+                ah[mt][3] = *reinterpret_cast<const uint32_t*>(s_xh + base + STEM_XP + 16);
+                al[mt][0] = *reinterpret_cast<const uint32_t*>(s_xl + base);
+                al[mt][1] = *reinterpret_cast<const uint32_t*>(s_xl + base + 16);
+                al[mt][2] = *reinterpret_cast<const uint32_t*>(s_xl + base + STEM_XP);
+                al[mt][3] = *reinterpret_cast<const uint32_t*>(s_xl + base + STEM_XP + 16);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int wb = (nt * 8 + g) * STEM_WP + kt * 16 + 2 * tg;
+                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(s_wh + wb);
+                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(s_wh + wb + 8);
+                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(s_wl + wb);
+                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(s_wl + wb + 8);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    mma_f16_16816(acc[mt][nt], ah[mt], bh0, bh1);
+                    mma_f16_16816(acc[mt][nt], al[mt], bh0, bh1);
+                    mma_f16_16816(acc[mt][nt], ah[mt], bl0, bl1);
+                }
+            }
+        }
+    }
+    uint32_t* stg = s_stage + warp * 1024;          // 32 pixels x 128 B
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+        const int ho = ho0 + 2 * warp + mt;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int ox = g + 8 * half;
+                const int ch = nt * 8 + 2 * tg;
+                float v0 = acc[mt][nt][half * 2], v1 = acc[mt][nt][half * 2 + 1];
+                if (add) {
+                    const float2 a2 = *reinterpret_cast<const float2*>(add + (((size_t)b * Ho + ho) * Wo + wo0 + ox) * 64 + ch);
+                    v0 += a2.x;
+                    v1 += a2.y;
+                }
+                v0 += s_vec[ch];
+                v1 += s_vec[ch + 1];
+                const int p = mt * 16 + ox;
+                stg[p * 32 + ((nt * 4 + tg) ^ ((p & 7) << 2))] = pack_h2(v0, v1);
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int idx = it * 32 + lane;
+        const int p = idx >> 3, chunk = idx & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + p * 32 + ((chunk ^ (p & 7)) << 2));
+        const int ho = ho0 + 2 * warp + (p >> 4), wo = wo0 + (p & 15);
+        *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + ho) * Wo + wo) * 64 + chunk * 8) = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ InstanceNorm
 // Statistics of an NHWC f16 tensor per (sample, channel) plane -> stats[b][c] = {mean, rstd} (biased variance, eps 1e-5:
 // InstanceNorm2d defaults, modules_DANRA_conditional.py:409,417).  Deterministic two-level reduction without float
