@@ -381,6 +381,12 @@ static int pack_family_r(Handle* h) {
         if (w->shape[0] != h->cfg.c_out || w->shape[1] != 64) return fail(-3, "final_layer.conv.weight shape mismatch");
         B2D_TRY(upload_f32(h, "tail.w", w->v));
         B2D_TRY(upload_f32(h, "tail.b", b->v));
+        // K-major copy for the tensor-core tail: [n][tap * 64 + c]
+        std::vector<float> wk((size_t)h->cfg.c_out * 576);
+        for (int n = 0; n < h->cfg.c_out; ++n)
+            for (int c = 0; c < 64; ++c)
+                for (int tap = 0; tap < 9; ++tap) wk[(size_t)n * 576 + tap * 64 + c] = w->v[((size_t)n * 64 + c) * 9 + tap];
+        B2D_TRY(upload_f32(h, "tail.wk", wk));
     }
     return 0;
 }
@@ -726,11 +732,16 @@ static int build_program_r(Handle* h, int B) {
         Handle* hh = h;
         const float* tw = bd.W<float>("tail.w");
         const float* tb = bd.W<float>("tail.b");
+        const float* twk = bd.W<float>("tail.wk");
         const int cout = c.c_out, Hh = H;
         ops.meta("final.conv", "tail_conv", 2.0 * B * Hh * Hh * 576 * cout, (double)B * Hh * Hh * (64 * 2 + 4 * cout));
         ops.push_back([=](cudaStream_t s2) {
             dim3 grid((Hh + 31) / 32, (Hh + 7) / 8, B);
-            B2D_CUDA(launch_k(tail_conv_kernel, dim3(grid), dim3(256), TAIL_SMEM, s2, up, st, tw, tb, hh->cur_eps, Hh, Hh, cout));
+            static const bool simt_tail = getenv("B2D_SIMT_TAIL") != nullptr;
+            if (cout <= 8 && !simt_tail)
+                B2D_CUDA(launch_k(tail_mma_kernel, dim3(grid), dim3(256), TAILM_SMEM, s2, up, st, twk, tb, hh->cur_eps, Hh, Hh, cout));
+            else
+                B2D_CUDA(launch_k(tail_conv_kernel, dim3(grid), dim3(256), TAIL_SMEM, s2, up, st, tw, tb, hh->cur_eps, Hh, Hh, cout));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -772,6 +783,7 @@ static int init_uniform_carveout() {
     B2D_TRY(set_carveout(temb_project_kernel));
     B2D_TRY(set_carveout(stem_conv_kernel<8, 2>));
     B2D_CUDA(cudaFuncSetAttribute(stem_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_MMA_SMEM));
+    B2D_CUDA(cudaFuncSetAttribute(tail_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAILM_SMEM));
     B2D_TRY(set_carveout(stem_conv_kernel<3, 1>));
     B2D_TRY(set_carveout(plane_stats_kernel));
     B2D_TRY(set_carveout(instnorm_apply_kernel));

@@ -25,38 +25,50 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
                                                            int n_enc, int n_out, int B, int t_off) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float se[TEMB_SB][TEMB_DIM], sd[TEMB_SB][TEMB_DIM];
+    __shared__ float se[TEMB_SB][TEMB_DIM];   // silu(embedding) of this CTA's samples (encoder OR decoder flavour)
     const int b0 = blockIdx.y * TEMB_SB;
     const int o0 = blockIdx.x * TEMB_OC;
-    const bool need_enc = o0 < n_enc, need_dec = o0 + TEMB_OC > n_enc;
+    const bool enc = o0 < n_enc;              // n_enc is a multiple of TEMB_OC (host-checked): a CTA is all-encoder or all-decoder
     {
         const int k = threadIdx.x;  // 256 threads <-> 256 embedding entries
-        const int j = k & 127;
-        const float inv = enc_inv[j], div = dec_div[k >> 1];
+        // inside the reverse loop every sample carries the same t: the sin/cos is evaluated once and reused
+        const int t0 = t[min(b0, B - 1)] + t_off;   // t_off = -1: embeddings of the NEXT reverse step
+        auto emb = [&](int tt) -> float {
+            const float tf = (float)tt;
+            if (enc) {
+                const float a = tf * enc_inv[k & 127];
+                return (k < 128) ? sinf(a) : cosf(a);
+            }
+            const float a2 = __fdiv_rn(tf, dec_div[k >> 1]);
+            return (k & 1) ? cosf(a2) : sinf(a2);
+        };
+        const float e0 = emb(t0);
+        const bool labelled = enc && label_emb != nullptr && y != nullptr;
+        const float s0 = silu(e0);
 #pragma unroll
         for (int sidx = 0; sidx < TEMB_SB; ++sidx) {
             const int b = min(b0 + sidx, B - 1);
-            const float tf = (float)(t[b] + t_off);   // t_off = -1: embeddings of the NEXT reverse step
-            if (need_enc) {
-                const float a = tf * inv;
-                float e = (k < 128) ? sinf(a) : cosf(a);
-                if (label_emb != nullptr && y != nullptr) e += label_emb[(size_t)y[b] * TEMB_DIM + k];
-                se[sidx][k] = silu(e);
-            }
-            if (need_dec) {
-                const float a2 = __fdiv_rn(tf, div);
-                sd[sidx][k] = silu((k & 1) ? cosf(a2) : sinf(a2));
-            }
+            const int tb = t[b] + t_off;
+            float e = (tb == t0) ? e0 : emb(tb);
+            float sv = s0;
+            if (labelled) sv = silu(e + label_emb[(size_t)y[b] * TEMB_DIM + k]);
+            else if (tb != t0) sv = silu(e);
+            se[sidx][k] = sv;
         }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll 1
+    // this lane's slice of the 8 embeddings stays in registers for all outputs of the warp
+    float ev[TEMB_SB][8];
+#pragma unroll
+    for (int sidx = 0; sidx < TEMB_SB; ++sidx)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ev[sidx][q] = se[sidx][lane + 32 * q];
+#pragma unroll 2
     for (int oi = 0; oi < TEMB_OC / 8; ++oi) {
         const int o = o0 + warp * (TEMB_OC / 8) + oi;
         if (o >= n_out) break;
         const float* w = W + (size_t)o * TEMB_DIM;
-        const float(*e)[TEMB_DIM] = (o < n_enc) ? se : sd;
         float wv[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) wv[q] = __ldg(w + lane + 32 * q);
@@ -65,15 +77,36 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
         for (int sidx = 0; sidx < TEMB_SB; ++sidx) {
             float a = 0.f;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) a = fmaf(wv[q], e[sidx][lane + 32 * q], a);
-            acc[sidx] = warp_sum(a);
+            for (int q = 0; q < 8; ++q) a = fmaf(wv[q], ev[sidx][q], a);
+            acc[sidx] = a;
         }
-        if (lane < TEMB_SB && b0 + lane < B) {
-            float v = acc[0];
+        // transposed butterfly: 8 per-lane partials -> lane L ends with the total of sample ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1)
+        float r4[4], r2[2], r1;
+        {
+            const bool up = lane & 16;
 #pragma unroll
-            for (int sidx = 1; sidx < TEMB_SB; ++sidx) v = (lane == sidx) ? acc[sidx] : v;
-            out[(size_t)(b0 + lane) * n_out + o] = v + bias[o];
+            for (int i = 0; i < 4; ++i) {
+                const float keep = up ? acc[4 + i] : acc[i], give = up ? acc[i] : acc[4 + i];
+                r4[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+            }
         }
+        {
+            const bool up = lane & 8;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float keep = up ? r4[2 + i] : r4[i], give = up ? r4[i] : r4[2 + i];
+                r2[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+            }
+        }
+        {
+            const bool up = lane & 4;
+            const float keep = up ? r2[1] : r2[0], give = up ? r2[0] : r2[1];
+            r1 = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+        }
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+        const int sidx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        if ((lane & 3) == 0 && b0 + sidx < B) out[(size_t)(b0 + sidx) * n_out + o] = r1 + bias[o];
     }
 }
 
@@ -190,15 +223,15 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 }
 
 // Tensor-core version of the per-step 8x8 / stride 2 / pad 3 stem (Encoder.conv1 on the diffusion state), used when the
-// output extent is a multiple of 16.  The fp32 state is NOT rounded: x and w are split into fp16 (hi, lo) pairs and the
-// product is formed as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulation (mma.sync m16n8k16; error ~2^-22).
+// output extent is a multiple of 16.  The fp32 state is NOT rounded: x is split into an fp16 (hi, lo) pair and the product is
+// formed as x_hi*w + x_lo*w with fp32 accumulation (mma.sync m16n8k16); the weights are fp16 like every other layer's.
 // CTA = 16x16 output pixels x 64 channels, 8 warps; warp = 2 output rows (two m16 tiles) x all 64 channels.
 // GEMM view per input channel: M = pixel, K = 64 taps (k-tile = two filter rows), N = 64.  The A fragments are plain
 // 32-bit shared-memory loads from the (38 x 38) input tile: tap (ky, kx) of output pixel (oy, ox) is tile[2oy+ky][2ox+kx],
 // and a fragment register holds two consecutive kx.  Epilogue: + precomputed conditioning part (fp32) + time projection,
 // fp16 rows staged per warp in swizzled shared memory and written as full 128-byte lines.
 constexpr int STEM_IT = 38, STEM_XP = 40, STEM_WP = 72;
-constexpr int STEM_MMA_SMEM = 2 * STEM_IT * STEM_XP * 2 + 2 * 64 * STEM_WP * 2 + 8 * 4096 + 64 * 4;
+constexpr int STEM_MMA_SMEM = 2 * STEM_IT * STEM_XP * 2 + 64 * STEM_WP * 2 + 8 * 4096 + 64 * 4;
 __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restrict__ in, int Cx, int Hi, int Wi,
                                                           const float* __restrict__ w,    // packed [Cin_total][64 taps][64]
                                                           const float* __restrict__ add,  // [B,Ho,Wo,64] fp32 or null
@@ -210,8 +243,7 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restric
     f16* s_xh = reinterpret_cast<f16*>(stem_smem);
     f16* s_xl = s_xh + STEM_IT * STEM_XP;
     f16* s_wh = s_xl + STEM_IT * STEM_XP;
-    f16* s_wl = s_wh + 64 * STEM_WP;
-    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_wl + 64 * STEM_WP);
+    uint32_t* s_stage = reinterpret_cast<uint32_t*>(s_wh + 64 * STEM_WP);
     float* s_vec = reinterpret_cast<float*>(s_stage + 8 * 1024);
     const int b = blockIdx.z;
     const int ho0 = blockIdx.y * 16, wo0 = blockIdx.x * 16;
@@ -240,9 +272,7 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restric
         for (int i = threadIdx.x; i < 4096; i += 256) {
             const int tap = i >> 6, n = i & 63;
             const float v = __ldg(wsrc + i);
-            const f16 hi = __float2half_rn(v);
-            s_wh[n * STEM_WP + tap] = hi;
-            s_wl[n * STEM_WP + tap] = __float2half_rn(v - __half2float(hi));
+            s_wh[n * STEM_WP + tap] = __float2half_rn(v);
         }
         __syncthreads();
 #pragma unroll 1
@@ -265,13 +295,10 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restric
                 const int wb = (nt * 8 + g) * STEM_WP + kt * 16 + 2 * tg;
                 const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(s_wh + wb);
                 const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(s_wh + wb + 8);
-                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(s_wl + wb);
-                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(s_wl + wb + 8);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     mma_f16_16816(acc[mt][nt], ah[mt], bh0, bh1);
                     mma_f16_16816(acc[mt][nt], al[mt], bh0, bh1);
-                    mma_f16_16816(acc[mt][nt], ah[mt], bl0, bl1);
                 }
             }
         }
@@ -507,6 +534,121 @@ __global__ void __launch_bounds__(256, 2) tail_conv_kernel(const f16* __restrict
                 if (h0 + i < H) out[(((size_t)b * c_out + oc) * H + h0 + i) * W + wcol] = acc[i] + bias[oc];
         }
     }
+}
+
+// Tensor-core version of the tail convolution for c_out <= 8.  GEMM view: M = output pixel, K = 9 taps x 64 channels, N = 8
+// (c_out real columns).  The InstanceNorm is folded into the weights per sample (w' = w * rstd, rounded to fp16 like every
+// other layer's weights) and its mean term becomes one constant per (output channel, tap), subtracted in the epilogue
+// for in-image taps only (zero padding applies to the NORMALISED tensor).  A fragments come straight from the cp.async-staged
+// (10 x 34 pixel) x 64-channel tile with ldmatrix (pixel pitch 144 B: conflict-free).  CTA = 8 x 32 output pixels, 8 warps,
+// warp = one output row = two m16 tiles.
+constexpr int TAILM_PP = 72;                 // halves per pixel in the tile (64 + 8 pad)
+constexpr int TAILM_WP = 584;                // halves per weight row (576 + 8 pad)
+constexpr int TAILM_SMEM = 10 * 34 * TAILM_PP * 2 + 8 * TAILM_WP * 2 + 8 * 9 * 4 + 128 * 4;
+__global__ void __launch_bounds__(256, 2) tail_mma_kernel(const f16* __restrict__ x,       // [B,H,W,64] (un-normalised)
+                                                          const float* __restrict__ stats,  // [B][64] x {mean, rstd}
+                                                          const float* __restrict__ w,      // K-major [c_out][tap * 64 + c]
+                                                          const float* __restrict__ bias, float* __restrict__ out,  // [B,c_out,H,W]
+                                                          int H, int W, int c_out) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(16) uint8_t tailm_smem[];
+    f16* tile = reinterpret_cast<f16*>(tailm_smem);                 // [10][34][72]
+    f16* s_wh = tile + 10 * 34 * TAILM_PP;                          // [8][584]
+    float* s_mt = reinterpret_cast<float*>(s_wh + 8 * TAILM_WP);    // [8][9] mean term per (output channel, tap)
+    float* s_st = s_mt + 72;                                        // [64] x {mean, rstd}
+    const int b = blockIdx.z;
+    const int w0 = blockIdx.x * 32, h0 = blockIdx.y * 8;
+    pdl_wait();
+    {   // tile load: thread = (16-byte channel chunk, column); columns 32/33 of each row by the first 160 threads
+        const int ch8 = threadIdx.x & 7, ixl = threadIdx.x >> 3;
+        const f16* xb = x + (size_t)b * H * W * 64 + ch8 * 8;
+        {
+            const int wi = w0 - 1 + ixl;
+            const bool cok = wi >= 0 && wi < W;
+#pragma unroll
+            for (int iy = 0; iy < 10; ++iy) {
+                const int hi = h0 - 1 + iy;
+                const bool ok = cok && hi >= 0 && hi < H;
+                cp_async16(tile + (size_t)(iy * 34 + ixl) * TAILM_PP + ch8 * 8, xb + ((size_t)(ok ? hi : 0) * W + (ok ? wi : 0)) * 64, ok);
+            }
+        }
+        if (threadIdx.x < 160) {
+            const int iy = threadIdx.x >> 4, ix = 32 + ((threadIdx.x >> 3) & 1);
+            const int hi = h0 - 1 + iy, wi = w0 - 1 + ix;
+            const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+            cp_async16(tile + (size_t)(iy * 34 + ix) * TAILM_PP + ch8 * 8, xb + ((size_t)(ok ? hi : 0) * W + (ok ? wi : 0)) * 64, ok);
+        }
+    }
+    cp_async_commit();
+    if (threadIdx.x < 128) s_st[threadIdx.x] = stats[(size_t)b * 128 + threadIdx.x];
+    {   // rows n >= c_out of the B operand are zero
+        uint4* z = reinterpret_cast<uint4*>(s_wh + (size_t)c_out * TAILM_WP);
+        const int nz = (8 - c_out) * TAILM_WP / 8;
+        for (int i = threadIdx.x; i < nz; i += 256) z[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    // folded weights: w is K-major [n][tap * 64 + c]
+    const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+    for (int n = 0; n < c_out; ++n) {
+        for (int k = threadIdx.x; k < 576; k += 256)
+            s_wh[n * TAILM_WP + k] = __float2half_rn(__ldg(w + (size_t)n * 576 + k) * s_st[2 * (k & 63) + 1]);
+        for (int tap = warp_; tap < 9; tap += 8) {
+            const float* wr = w + (size_t)n * 576 + tap * 64;
+            float m = __ldg(wr + lane_) * s_st[2 * lane_ + 1] * s_st[2 * lane_] +
+                      __ldg(wr + lane_ + 32) * s_st[2 * (lane_ + 32) + 1] * s_st[2 * (lane_ + 32)];
+            m = warp_sum(m);
+            if (lane_ == 0) s_mt[n * 9 + tap] = m;
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tg = lane & 3;
+    float acc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+    // ldmatrix row address of this lane: pixel (lane & 7) + 8 * ((lane >> 3) & 1), channel offset 8 * (lane >> 4)
+    const int lpix = (lane & 7) + ((lane >> 3) & 1) * 8, lch = (lane >> 4) * 8;
+    const uint32_t tile_u = smem_u32(tile);
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap - ky * 3;
+        const uint32_t rowbase = tile_u + (uint32_t)((((warp + ky) * 34) + kx + lpix) * TAILM_PP + lch) * 2;
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc) {
+            uint32_t a0[4], a1[4];
+            ldmatrix_x4(a0, rowbase + kc * 32);
+            ldmatrix_x4(a1, rowbase + 16 * TAILM_PP * 2 + kc * 32);
+            const int wb = g * TAILM_WP + tap * 64 + kc * 16 + 2 * tg;
+            const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(s_wh + wb);
+            const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(s_wh + wb + 8);
+            mma_f16_16816(acc[0], a0, bh0, bh1);
+            mma_f16_16816(acc[1], a1, bh0, bh1);
+        }
+    }
+    const int ho = h0 + warp;
+    if (ho >= H) return;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int wo = w0 + mt * 16 + g + 8 * half;
+            if (wo >= W) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int n = 2 * tg + j;
+                if (n >= c_out) continue;
+                float corr = 0.f;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int hi = ho + tap / 3 - 1, wi = wo + tap % 3 - 1;
+                    if (hi >= 0 && hi < H && wi >= 0 && wi < W) corr += s_mt[n * 9 + tap];
+                }
+                out[(((size_t)b * c_out + n) * H + ho) * W + wo] = acc[mt][half * 2 + j] - corr + bias[n];
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ posterior update
