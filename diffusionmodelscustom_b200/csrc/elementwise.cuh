@@ -340,35 +340,41 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------ InstanceNorm
 // Statistics of an NHWC f16 tensor per (sample, channel) plane -> stats[b][c] = {mean, rstd} (biased variance, eps 1e-5:
 // InstanceNorm2d defaults, modules_DANRA_conditional.py:409,417).  Deterministic two-level reduction without float
-// atomics: every CTA (32 channel-pair lanes x 8 pixel lanes over a slab of pixels) writes its partial {sum, sumsq};
+// atomics: every CTA (8 channel chunks of 16 B x 32 pixel lanes over a slab of pixels) writes its partial {sum, sumsq};
 // the last CTA to arrive for a (sample, 64-channel group) adds the partials in slab order and publishes mean/rstd.
 __global__ void __launch_bounds__(256) plane_stats_kernel(const f16* __restrict__ x, float* __restrict__ partial,
                                                           unsigned int* __restrict__ counters, float* __restrict__ stats,
                                                           int HW, int C, int pix_per_cta) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float s_sum[8][64], s_sq[8][64];
+    __shared__ float s_sum[32][65], s_sq[32][65];
     __shared__ bool s_last;
     const int b = blockIdx.z, grp = blockIdx.y, ngrp = gridDim.y, nslab = gridDim.x, slab = blockIdx.x;
     const int c0 = grp * 64;
-    const int cl = (threadIdx.x & 31) * 2, pl = threadIdx.x >> 5;
+    const int cg8 = (threadIdx.x & 7) * 8, pl = threadIdx.x >> 3;     // 16-byte channel chunk x 32 pixel lanes
     const int p0 = slab * pix_per_cta;
     const int p1 = min(p0 + pix_per_cta, HW);
-    float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
-    const f16* xb = x + (size_t)b * HW * C + c0 + cl;
-    for (int p = p0 + pl; p < p1; p += 8) {
-        const float2 v = __half22float2(*reinterpret_cast<const f162*>(xb + (size_t)p * C));
-        a0 += v.x; a1 += v.y;
-        q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+    float a[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
+    const f16* xb = x + (size_t)b * HW * C + c0 + cg8;
+#pragma unroll 4
+    for (int p = p0 + pl; p < p1; p += 32) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xb + (size_t)p * C);
+        float2 t;
+        t = unpack_h2(v.x); a[0] += t.x; a[1] += t.y; q[0] = fmaf(t.x, t.x, q[0]); q[1] = fmaf(t.y, t.y, q[1]);
+        t = unpack_h2(v.y); a[2] += t.x; a[3] += t.y; q[2] = fmaf(t.x, t.x, q[2]); q[3] = fmaf(t.y, t.y, q[3]);
+        t = unpack_h2(v.z); a[4] += t.x; a[5] += t.y; q[4] = fmaf(t.x, t.x, q[4]); q[5] = fmaf(t.y, t.y, q[5]);
+        t = unpack_h2(v.w); a[6] += t.x; a[7] += t.y; q[6] = fmaf(t.x, t.x, q[6]); q[7] = fmaf(t.y, t.y, q[7]);
     }
-    s_sum[pl][cl] = a0; s_sum[pl][cl + 1] = a1;
-    s_sq[pl][cl] = q0;  s_sq[pl][cl + 1] = q1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s_sum[pl][cg8 + j] = a[j]; s_sq[pl][cg8 + j] = q[j]; }
     __syncthreads();
     float* part = partial + ((size_t)(b * ngrp + grp) * nslab) * 128;
     if (threadIdx.x < 64) {
         float s = 0.f, q = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
+        for (int i = 0; i < 32; ++i) { s += s_sum[i][threadIdx.x]; q += s_sq[i][threadIdx.x]; }
         part[(size_t)slab * 128 + threadIdx.x] = s;
         part[(size_t)slab * 128 + 64 + threadIdx.x] = q;
         __threadfence();
@@ -380,9 +386,16 @@ __global__ void __launch_bounds__(256) plane_stats_kernel(const f16* __restrict_
     __threadfence();
     if (threadIdx.x < 64) {
         float s = 0.f, q = 0.f;
-        for (int i = 0; i < nslab; ++i) {
-            s += __ldcg(part + (size_t)i * 128 + threadIdx.x);
-            q += __ldcg(part + (size_t)i * 128 + 64 + threadIdx.x);
+        for (int i0 = 0; i0 < nslab; i0 += 16) {       // 32 independent loads in flight, then summed in slab order
+            float vs[16], vq[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const bool ok = i0 + j < nslab;
+                vs[j] = ok ? __ldcg(part + (size_t)(i0 + j) * 128 + threadIdx.x) : 0.f;
+                vq[j] = ok ? __ldcg(part + (size_t)(i0 + j) * 128 + 64 + threadIdx.x) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { s += vs[j]; q += vq[j]; }
         }
         const float inv = 1.0f / (float)HW;
         const float mean = s * inv;

@@ -86,18 +86,25 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const f16* __restrict
     }
     __syncthreads();
     if (!s_last) return;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
         __threadfence();
         double ts = 0.0, tq = 0.0;   // few dozen partials: fp64 here costs nothing and removes the cancellation worry
-        for (int i = 0; i < nslab; ++i) {
+        for (int i = threadIdx.x; i < nslab; i += 32) {   // lane-parallel loads, fixed reduction tree => deterministic
             ts += (double)__ldcg(partial + ((size_t)b * nslab + i) * 2);
             tq += (double)__ldcg(partial + ((size_t)b * nslab + i) * 2 + 1);
         }
-        const double mean = ts / (double)per_sample;
-        const double var = fmax(tq / (double)per_sample - mean * mean, 0.0);
-        stats[b * 2] = (float)mean;
-        stats[b * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
-        counters[b] = 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ts += __shfl_xor_sync(0xffffffffu, ts, o);
+            tq += __shfl_xor_sync(0xffffffffu, tq, o);
+        }
+        if (threadIdx.x == 0) {
+            const double mean = ts / (double)per_sample;
+            const double var = fmax(tq / (double)per_sample - mean * mean, 0.0);
+            stats[b * 2] = (float)mean;
+            stats[b * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+            counters[b] = 0u;
+        }
     }
 }
 
