@@ -44,9 +44,9 @@ WORKLOADS = {
 
 
 # DRAM bytes per launch (dram__bytes via ncu, cold-cache, averaged over the launches of the class) for the cfg2 step at batch 64:
-# profiles/r1_ncu_step_cfg2_b64_sections.txt.  Reported as roofline.traffic for that workload only.
-NCU_TRAFFIC_CFG2 = {"conv_tc": 3.57e6, "attn_tc": 15.76e6, "gemm_stream": None, "norm_fused": None, "layernorm": 5.6e6,
-                    "tail_conv": 33.6e6, "stem_conv": 17.9e6}
+# profiles/r1_ncu_step_cfg2_b64_final_sections.txt.  Reported as roofline.traffic for that workload only.
+NCU_TRAFFIC_CFG2 = {"conv_tc": 2.75e6, "attn_tc": 16.81e6, "gemm_stream": 7.89e6, "norm_fused": 5.01e6, "layernorm": 0.69e6,
+                    "tail_conv": 33.6e6, "stem_conv": 17.9e6, "plane_stats": 33.6e6, "temb_project": 1.65e6}
 
 
 def peaks():
@@ -283,7 +283,7 @@ def main():
         roof["algorithmic_bytes_per_launch"] = tk["bytes"] / tk["launches"]
         if args.workload == "cfg2" and batch == 64:
             roof["traffic"] = NCU_TRAFFIC_CFG2.get(tname)
-            roof["traffic_source"] = "profiles/r1_ncu_step_cfg2_b64_sections.txt (ncu dram bytes per launch, cold cache)"
+            roof["traffic_source"] = "profiles/r1_ncu_step_cfg2_b64_final_sections.txt (ncu dram bytes per launch, cold cache)"
         whole = value * flops_per_sample_step * (T_STEPS - 1) / 1e12 / world
         cpu = None
         if not args.no_cpu_baseline:
