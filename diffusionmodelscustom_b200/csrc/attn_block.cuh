@@ -1,0 +1,385 @@
+// Fused low-resolution self-attention: LayerNorm + QKV projection + softmax(QK^T)V for the levels with L = H*W <= 64 tokens
+// (ImageSelfAttention at 8x8, 4x4, 2x2, 1x1: modules_DANRA_conditional.py:91-110; unet_ms.py:6-27), one launch instead of
+// LayerNorm / QKV GEMM / attention.  The out-projection (+ residual) stays on conv_tc.
+//
+// CTA = (tile of 128 consecutive tokens = 128/L whole samples, one head).  All MMAs are tcgen05 with accumulators in TMEM:
+//   1. QKV_h = x W'_h^T over K = C in 64-wide k-blocks (TMA ring; A = raw activations, B = the head's D rows of the
+//      gamma-folded Wq, Wk, Wv as one 3-D TMA box) -> TMEM columns [0,3D).  The epilogue warps read the A stages as they pass
+//      and derive each row's LayerNorm mean / rstd, which is applied algebraically at read-out: rstd*acc - rstd*mu*c1 + b'.
+//   2. read-out (thread = token row): Q (pre-scaled by log2(e)/sqrt(D)) and K are written to shared memory as 128B-swizzled
+//      K-major operands, V is written TRANSPOSED ([D][128 keys]) so that it is a K-major B operand for P.V.
+//   3. S = Q K^T for the whole tile (128 x 128); each row only uses the L columns of its own sample (block-diagonal mask),
+//      softmax in registers, P (fp16, zero outside the sample) goes back to TMEM and is the A operand of O = P V.
+//   4. O / rowsum -> fp16 -> global [rows][C] at the head's columns.
+// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: statistics / read-out / softmax (two warps per TMEM
+// lane quarter, splitting the columns).
+#pragma once
+#include "common.cuh"
+#include "conv.cuh"
+
+namespace b2d {
+
+constexpr int AB_THREADS = 320;
+template <int D>
+__host__ __device__ constexpr int ab_stages() { return D == 128 ? 3 : 4; }
+template <int D>
+__host__ __device__ constexpr int ab_stage_bytes() { return CONV_A_BYTES + 3 * D * 128; }
+template <int D>
+__host__ __device__ constexpr int ab_dpad() { return D < 64 ? 64 : D; }
+template <int D>
+__host__ __device__ constexpr int ab_smem_bytes() { return 1024 + ab_stages<D>() * ab_stage_bytes<D>() + 3 * D * 8 + 128 * 16 + 128 * 4 + 256; }
+
+struct AttnBlockParams {
+    const float* c1;     // [3C] column sums of the gamma-folded weights
+    const float* bias;   // [3C] folded bias
+    f16* out;            // [M][C] attention output (before the out-projection)
+    int M, C, L;
+    float scale_log2e;
+};
+
+template <int D>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+    attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AttnBlockParams p) {
+    pdl_launch_dependents();
+    constexpr int STAGES = ab_stages<D>();
+    constexpr int SB = ab_stage_bytes<D>();
+    constexpr int DPAD = ab_dpad<D>();
+    constexpr int S_COL = 384, P_COL = 0, O_COL = 64;
+    extern __shared__ uint8_t ab_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ab_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = smem;
+    // operands of the attention phase alias the (drained) ring
+    uint8_t* sQ = ring;                                         // DPAD/64 atoms of [128 rows][128 B]
+    uint8_t* sK = sQ + (DPAD / 64) * CONV_A_BYTES;
+    uint8_t* sVt = sK + (DPAD / 64) * CONV_A_BYTES;             // 2 atoms (keys 0-63, 64-127) of [D rows][128 B]
+    static_assert(2 * (DPAD / 64) * CONV_A_BYTES + 2 * D * 128 <= STAGES * SB, "attention operands must fit the ring");
+    float* s_c1 = reinterpret_cast<float*>(ring + STAGES * SB);  // [3D]
+    float* s_bias = s_c1 + 3 * D;                                // [3D]
+    float2* s_stat = reinterpret_cast<float2*>(s_bias + 3 * D);  // [2][128]
+    float* s_l = reinterpret_cast<float*>(s_stat + 256);         // [128] softmax denominators
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_l + 128);
+    uint64_t* full = bars;                // [STAGES]
+    uint64_t* empty = bars + STAGES;      // [STAGES]
+    uint64_t* accum_full = bars + 2 * STAGES;
+    uint64_t* qk_ready = accum_full + 1;
+    uint64_t* s_full = accum_full + 2;
+    uint64_t* p_ready = accum_full + 3;
+    uint64_t* o_full = accum_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+    const int m0 = blockIdx.x * 128;
+    const int nkb = p.C >> 6;
+
+    for (int i = threadIdx.x; i < 3 * D; i += AB_THREADS) {
+        const int mat = i / D, d = i - mat * D;
+        s_c1[i] = __ldg(p.c1 + mat * p.C + head * D + d);
+        s_bias[i] = __ldg(p.bias + mat * p.C + head * D + d);
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_init(&full[i], 1);
+                mbar_init(&empty[i], 1 + 8);     // MMA commit + the eight statistics warps
+            }
+            mbar_init(accum_full, 1);
+            mbar_init(qk_ready, 8);
+            mbar_init(s_full, 1);
+            mbar_init(p_ready, 4);
+            mbar_init(o_full, 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&full[st], SB);
+                tma_load_2d(ring + st * SB, &tmA, &full[st], kb * 64, m0);
+                tma_load_3d(ring + st * SB + CONV_A_BYTES, &tmB, &full[st], kb * 64, head * D, 0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- 1. QKV projection
+            constexpr int N1 = (3 * D <= 256) ? 3 * D : 256;
+            constexpr uint32_t idesc1 = umma_idesc_f16(128, N1);
+            constexpr uint32_t idesc2 = umma_idesc_f16(128, 3 * D - N1 > 0 ? 3 * D - N1 : 16);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % STAGES;
+                mbar_wait(&full[st], (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint64_t da = umma_desc_sw128(smem_u32(ring + st * SB));
+                const uint64_t db = umma_desc_sw128(smem_u32(ring + st * SB + CONV_A_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    umma_f16(tmem, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kb | k) != 0);
+                    if (3 * D > N1) {
+                        const uint64_t db2 = umma_desc_sw128(smem_u32(ring + st * SB + CONV_A_BYTES + N1 * 128));
+                        umma_f16(tmem + N1, da + (uint64_t)(k * 2), db2 + (uint64_t)(k * 2), idesc2, (kb | k) != 0);
+                    }
+                }
+                umma_commit(&empty[st]);
+            }
+            umma_commit(accum_full);
+            // ---- 3. S = Q K^T
+            mbar_wait(qk_ready, 0);
+            tc_fence_after();
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, 128);
+#pragma unroll
+            for (int kk = 0; kk < DPAD / 16; ++kk) {
+                const uint64_t dq = umma_desc_sw128(smem_u32(sQ + (kk >> 2) * CONV_A_BYTES)) + (uint64_t)((kk & 3) * 2);
+                const uint64_t dk = umma_desc_sw128(smem_u32(sK + (kk >> 2) * CONV_A_BYTES)) + (uint64_t)((kk & 3) * 2);
+                umma_f16(tmem + S_COL, dq, dk, idesc_s, kk != 0);
+            }
+            umma_commit(s_full);
+            // ---- O = P V
+            mbar_wait(p_ready, 0);
+            tc_fence_after();
+            constexpr uint32_t idesc_o = umma_idesc_f16(128, D);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const uint64_t dv = umma_desc_sw128(smem_u32(sVt + (kk >> 2) * (D * 128))) + (uint64_t)((kk & 3) * 2);
+                umma_f16_ts(tmem + O_COL, tmem + P_COL + kk * 8, dv, idesc_o, kk != 0);
+            }
+            umma_commit(o_full);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int hf = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int sw = row & 7;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        // ---- LayerNorm statistics from the A stages (each half-warp-group sums 4 of the 8 chunks of a 64-channel block)
+        float s1 = 0.f, s2 = 0.f;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % STAGES;
+            mbar_wait(&full[st], (kb / STAGES) & 1);
+            const uint4* arow = reinterpret_cast<const uint4*>(ring + st * SB + row * 128);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const uint4 a4 = arow[(hf * 4 + jj) ^ sw];
+                float2 tt;
+                tt = unpack_h2(a4.x); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                tt = unpack_h2(a4.y); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                tt = unpack_h2(a4.z); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+                tt = unpack_h2(a4.w); s1 += tt.x + tt.y; s2 = fmaf(tt.x, tt.x, s2); s2 = fmaf(tt.y, tt.y, s2);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        s_stat[hf * 128 + row] = make_float2(s1, s2);
+        named_bar_sync(1, 256);
+        float ln_a, ln_b;
+        {
+            const float2 v0 = s_stat[row], v1 = s_stat[128 + row];
+            const float invk = 1.0f / (float)p.C;
+            const float mu = (v0.x + v1.x) * invk;
+            ln_a = rsqrtf(fmaxf((v0.y + v1.y) * invk - mu * mu, 0.f) + 1e-5f);
+            ln_b = -ln_a * mu;
+        }
+        // ---- 2. read-out of Q, K, V (32-column chunks, alternating between the two warps of a lane quarter)
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        constexpr int CPM = D / 32;                                // chunks per matrix
+#pragma unroll 1
+        for (int c = hf; c < 3 * CPM; c += 2) {
+            const int mat = c / CPM, col0 = (c - mat * CPM) * 32;
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_off + (uint32_t)(mat * D + col0), v);
+            tmem_ld_wait();
+            float f[32];
+            const float post = (mat == 0) ? p.scale_log2e : 1.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int ci = mat * D + col0 + j;
+                f[j] = fmaf(ln_a, __uint_as_float(v[j]), fmaf(ln_b, s_c1[ci], s_bias[ci])) * post;
+            }
+            if (mat < 2) {
+                uint8_t* base = (mat == 0 ? sQ : sK) + (col0 >> 6) * CONV_A_BYTES + row * 128;
+                const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 o;
+                    o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
+                    o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
+                    o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
+                    o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
+                    *reinterpret_cast<uint4*>(base + (((ch0 + j) ^ sw) << 4)) = o;
+                }
+            } else {
+                // V^T: element (d, key = row) of atom row>>6: [d][128 B], 16-byte chunk ((row & 63) >> 3) ^ (d & 7)
+                uint8_t* base = sVt + (row >> 6) * (D * 128) + (row & 7) * 2;
+                const int kc = (row & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int d = col0 + j;
+                    *reinterpret_cast<f16*>(base + d * 128 + ((kc ^ (d & 7)) << 4)) = __float2half_rn(fminf(fmaxf(f[j], -65504.f), 65504.f));
+                }
+            }
+        }
+        if (D < 64 && hf == 1) {   // zero the K padding (columns D..63) of this row in Q and K
+#pragma unroll
+            for (int j = D / 8; j < 8; ++j) {
+                *reinterpret_cast<uint4*>(sQ + row * 128 + ((j ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(sK + row * 128 + ((j ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(qk_ready);
+        // ---- 3. block-diagonal softmax (one thread per row; the hf == 0 warps)
+        if (hf == 0) {
+            mbar_wait(s_full, 0);
+            tc_fence_after();
+            const int L = p.L;
+            const int span = L > 32 ? 64 : 32;                       // columns this warp loads
+            const int col_base = L > 32 ? (row / L) * L : q * 32;    // warp-uniform
+            uint32_t v[2][32];
+            tmem_ld32(tmem + lane_off + (uint32_t)(S_COL + col_base), v[0]);
+            if (span == 64) tmem_ld32(tmem + lane_off + (uint32_t)(S_COL + col_base + 32), v[1]);
+            tmem_ld_wait();
+            const int own0 = (row / L) * L - col_base;               // first valid column (relative), L valid columns
+            float mx = -INFINITY;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int cj = hh * 32 + j;
+                    const bool ok = cj < span && cj >= own0 && cj < own0 + L;
+                    if (ok) mx = fmaxf(mx, __uint_as_float(v[hh][j]));
+                }
+            float lsum = 0.f;
+            uint32_t pk[2][16];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c0 = hh * 32 + 2 * j, c1 = c0 + 1;
+                    const bool ok0 = c0 < span && c0 >= own0 && c0 < own0 + L;
+                    const bool ok1 = c1 < span && c1 >= own0 && c1 < own0 + L;
+                    const float p0 = ok0 ? ex2_approx(__uint_as_float(v[hh][2 * j]) - mx) : 0.f;
+                    const float p1 = ok1 ? ex2_approx(__uint_as_float(v[hh][2 * j + 1]) - mx) : 0.f;
+                    lsum += p0 + p1;
+                    pk[hh][j] = pack_h2_nosat(p0, p1);
+                }
+            s_l[row] = lsum;
+            // P: 128 keys = 64 packed columns = 4 chunks of 16; zero outside this row's sample
+            uint32_t zero[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) zero[j] = 0u;
+            const int cb = col_base >> 5;                             // first loaded 32-key chunk
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                const uint32_t addr = tmem + lane_off + (uint32_t)(P_COL + ch * 16);
+                if (ch == cb) tmem_st16(addr, pk[0]);
+                else if (span == 64 && ch == cb + 1) tmem_st16(addr, pk[1]);
+                else tmem_st16(addr, zero);
+            }
+            tmem_st_wait();
+            __threadfence_block();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);
+        }
+        // ---- 4. O / l -> fp16 -> global
+        mbar_wait(o_full, 0);
+        tc_fence_after();
+        constexpr int OCH = D / 32;                                 // 32-column chunks of O
+        const float inv = 1.0f / s_l[row];
+        const int grow = m0 + row;
+#pragma unroll 1
+        for (int c = hf; c < OCH; c += 2) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_off + (uint32_t)(O_COL + c * 32), v);
+            tmem_ld_wait();
+            if (grow < p.M) {
+                uint4* op = reinterpret_cast<uint4*>(p.out + (size_t)grow * p.C + head * D + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 o;
+                    o.x = pack_h2(__uint_as_float(v[j * 8 + 0]) * inv, __uint_as_float(v[j * 8 + 1]) * inv);
+                    o.y = pack_h2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv);
+                    o.z = pack_h2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv);
+                    o.w = pack_h2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv);
+                    op[j] = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+struct AttnBlockPlan {
+    CUtensorMap tmA, tmB;
+    AttnBlockParams p;
+    int D = 0, heads = 0;
+};
+
+inline bool attn_block_supported(int L, int C, int heads) {
+    if (heads <= 0 || C % heads != 0 || C % 64 != 0) return false;
+    const int D = C / heads;
+    if (D != 32 && D != 64 && D != 128) return false;
+    return L >= 1 && L <= 64 && (128 % L) == 0;
+}
+
+// x: [M][C] fp16 activations (raw, un-normalised); w: gamma-folded in_proj weight [3C][C] fp16.
+inline int attn_block_plan_build(AttnBlockPlan& pl, const f16* x, const f16* w, const float* c1, const float* bias, f16* out, int M,
+                                 int C, int L, int heads) {
+    pl.D = C / heads;
+    pl.heads = heads;
+    pl.p.c1 = c1; pl.p.bias = bias; pl.p.out = out; pl.p.M = M; pl.p.C = C; pl.p.L = L;
+    pl.p.scale_log2e = 1.4426950408889634f / sqrtf((float)pl.D);
+    uint64_t ad[2] = {(uint64_t)C, (uint64_t)M};
+    uint64_t as[1] = {(uint64_t)C * 2};
+    uint32_t ab[2] = {64, 128};
+    B2D_TRY(make_tmap_f16(&pl.tmA, x, 2, ad, as, ab));
+    uint64_t bd[3] = {(uint64_t)C, (uint64_t)C, 3};
+    uint64_t bs[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
+    uint32_t bb[3] = {64, (uint32_t)pl.D, 3};
+    B2D_TRY(make_tmap_f16(&pl.tmB, w, 3, bd, bs, bb));
+    return 0;
+}
+
+inline int attn_block_init_attrs() {
+    B2D_CUDA(cudaFuncSetAttribute(attn_block_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, ab_smem_bytes<32>()));
+    B2D_CUDA(cudaFuncSetAttribute(attn_block_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ab_smem_bytes<64>()));
+    B2D_CUDA(cudaFuncSetAttribute(attn_block_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ab_smem_bytes<128>()));
+    return 0;
+}
+
+inline int attn_block_launch(const AttnBlockPlan& pl, cudaStream_t st) {
+    const dim3 grid((pl.p.M + 127) / 128, pl.heads);
+    if (pl.D == 32)
+        B2D_CUDA(launch_k(attn_block_kernel<32>, grid, dim3(AB_THREADS), ab_smem_bytes<32>(), st, pl.tmA, pl.tmB, pl.p));
+    else if (pl.D == 64)
+        B2D_CUDA(launch_k(attn_block_kernel<64>, grid, dim3(AB_THREADS), ab_smem_bytes<64>(), st, pl.tmA, pl.tmB, pl.p));
+    else
+        B2D_CUDA(launch_k(attn_block_kernel<128>, grid, dim3(AB_THREADS), ab_smem_bytes<128>(), st, pl.tmA, pl.tmB, pl.p));
+    return 0;
+}
+
+}  // namespace b2d

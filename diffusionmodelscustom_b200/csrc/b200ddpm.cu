@@ -11,6 +11,7 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attn_block.cuh"
 #include "common.cuh"
 #include "conv.cuh"
 #include "elementwise.cuh"
@@ -287,8 +288,7 @@ static int pack_attention(Handle* h, const std::string& role, const std::string&
     B2D_TRY(upload_f32(h, role + ".ln.g", g->v));
     B2D_TRY(upload_f32(h, role + ".ln.b", b->v));
     B2D_TRY(pack_linear(h, role + ".qkv", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias"));
-    if (g->v.size() <= 128)
-        B2D_TRY(pack_ln_linear(h, role + ".qkvln", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias", g, b));
+    B2D_TRY(pack_ln_linear(h, role + ".qkvln", prefix + "." + mha + ".in_proj_weight", prefix + "." + mha + ".in_proj_bias", g, b));
     B2D_TRY(pack_linear(h, role + ".out", prefix + "." + mha + ".out_proj.weight", prefix + "." + mha + ".out_proj.bias"));
     if (h->cfg.attn_ff) {
         const std::string fp = prefix + "." + ffp;
@@ -499,7 +499,16 @@ struct Builder {
         // LayerNorm folded into the QKV / FF1 GEMM whenever that GEMM runs on the streaming kernel (C <= 128, enough rows)
         static const bool no_ln_fold = getenv("B2D_NO_LN_FOLD") != nullptr;
         const bool fold = !no_ln_fold && !h->cfg.debug_simt_conv && !getenv("B2D_NO_STREAM_GEMM") && C <= 128 && rows >= GS_MIN_ROWS;
-        if (fold) {
+        // low-resolution levels (L <= 64 tokens): LayerNorm + QKV + attention in ONE launch
+        static const bool no_attn_block = getenv("B2D_NO_ATTN_BLOCK") != nullptr;
+        const bool fused_block = !no_attn_block && !h->cfg.debug_simt_conv && attn_block_supported(L, C, heads);
+        if (fused_block) {
+            auto pl = std::make_shared<AttnBlockPlan>();
+            if (attn_block_plan_build(*pl, x, W<f16>(role + ".qkvln.w"), W<float>(role + ".qkvln.c1"), W<float>(role + ".qkvln.b"), ao,
+                                      rows, C, L, heads) != 0) { err = -1; return; }
+            ops.meta(role + ".attn", "attn_block", 6.0 * rows * C * C + 4.0 * (double)L * L * C * B, 4.0 * rows * C + 6.0 * C * C);
+            ops.push_back([=](cudaStream_t st) { return attn_block_launch(*pl, st); });
+        } else if (fold) {
             next_ln_c1 = W<float>(role + ".qkvln.c1");
             conv(x, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkvln", nullptr, nullptr, 0, 0);
         } else {
@@ -508,7 +517,9 @@ struct Builder {
             conv(xn, hw, hw, C, qkv, 3 * C, 1, 1, 0, false, role + ".qkv", nullptr, nullptr, 0, 0);
         }
         static const bool no_tc_attn = getenv("B2D_NO_TC_ATTN") != nullptr;
-        if (attn_tc_supported(L, C, heads) && !no_tc_attn) {
+        if (fused_block) {
+            // attention output already in `ao`
+        } else if (attn_tc_supported(L, C, heads) && !no_tc_attn) {
             auto tmq = std::make_shared<AttnTcMaps>();
             if (attn_tc_make_map(tmq.get(), qkv, B, L, C) != 0) { err = -1; return; }
             ops.meta(role + ".sdpa", "attn_tc", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
@@ -993,6 +1004,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = flash_attn_init_attrs())) break;
         if ((rc = attn_tc_init_attrs())) break;
         if ((rc = gemm_stream_init_attrs())) break;
+        if ((rc = attn_block_init_attrs())) break;
         if ((rc = norm_fused_init_attrs())) break;
         if ((rc = init_uniform_carveout())) break;
         const int B = cfg->max_batch, H = cfg->img_size;
@@ -1431,6 +1443,15 @@ int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, 
         return attn_tc_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
     }
     return flash_attn_launch((const f16*)qkv, (f16*)o, B, L, C, heads, as_stream(stream));
+}
+
+int b2d_op_attn_block(const void* x, const void* w_folded, const float* c1, const float* bias, void* o, int32_t B, int32_t L,
+                      int32_t C, int32_t heads, void* stream) {
+    B2D_CHECK(attn_block_supported(L, C, heads), "shape not eligible for the fused low-resolution attention");
+    B2D_TRY(attn_block_init_attrs());
+    AttnBlockPlan pl;
+    B2D_TRY(attn_block_plan_build(pl, (const f16*)x, (const f16*)w_folded, c1, bias, (f16*)o, B * L, C, L, heads));
+    return attn_block_launch(pl, as_stream(stream));
 }
 
 int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t vec_stride, void* y, float* stats_ws,

@@ -122,6 +122,12 @@ int b2d_op_conv2d(const void* in_f16, const void* w_packed_f16, const float* bia
 int b2d_op_layernorm(const void* x_f16, const float* gamma, const float* beta, void* y_f16, int32_t rows, int32_t C,
                      void* stream);
 int b2d_op_attention(const void* qkv_f16, void* o_f16, int32_t B, int32_t L, int32_t C, int32_t heads, void* stream);
+/* Fused low-resolution attention (L <= 64 tokens, 128 % L == 0, head_dim 32/64/128): LayerNorm + QKV projection + softmax(QK^T)V.
+ * w_folded: f16 [3C][C] = in_proj_weight * ln_gamma; c1[n] = sum_k w_folded[n][k]; bias[n] = in_proj_bias[n] + sum_k W[n][k]*ln_beta[k].
+ * Replaces nn.LayerNorm + the in-projection and scaled-dot-product part of nn.MultiheadAttention
+ * (modules_DANRA_conditional.py:100-107); the out-projection is a b2d_op_conv2d. */
+int b2d_op_attn_block(const void* x_f16, const void* w_folded_f16, const float* c1, const float* bias, void* o_f16,
+                      int32_t B, int32_t L, int32_t C, int32_t heads, void* stream);
 int b2d_op_instnorm(const void* x_f16, const void* skip_f16, const float* vec, int32_t vec_stride, void* y_f16,
                     float* stats_ws, int32_t B, int32_t HW, int32_t C, void* stream);
 int b2d_op_posterior_update(float* x, const float* eps, const float* z_or_null, const float* betas, const float* alphas,

@@ -140,6 +140,36 @@ def test_attention_matches_torch(case):
     assert G.rel_l2(o.float().cpu(), ref) < 3e-3     # P is rounded to fp16 before P.V
 
 
+ATTN_BLOCK_CASES = [(64, 64, 128, 4), (64, 16, 256, 4), (64, 4, 512, 4), (5, 4, 512, 4), (3, 16, 256, 4), (3, 64, 128, 4),
+                    (7, 1, 512, 4), (4, 16, 256, 8), (2, 64, 256, 8), (9, 2, 128, 4), (3, 32, 512, 8)]
+
+
+@pytest.mark.parametrize("case", ATTN_BLOCK_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}" for b, l, c, h in ATTN_BLOCK_CASES])
+def test_fused_lowres_attention_block(case):
+    """LayerNorm + in-projection + softmax(QK^T)V in one launch vs torch fp32 (nn.LayerNorm + nn.MultiheadAttention internals,
+    modules_DANRA_conditional.py:100-107) on the same fp16-rounded inputs."""
+    B, L, C, heads = case
+    d = C // heads
+    g = torch.Generator().manual_seed(7 * L + C + heads)
+    x = _bf(torch.randn(B, L, C, generator=g) * 1.7 + 0.4)
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    W = torch.randn(3 * C, C, generator=g) / math.sqrt(C)
+    bias = 0.1 * torch.randn(3 * C, generator=g)
+    xn = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    qkv = xn @ W.t() + bias
+    q, k, v = (t.reshape(B, L, heads, d).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), -1) @ v).permute(0, 2, 1, 3).reshape(B, L, C)
+    wf = (W * gamma[None, :]).to(torch.float16)
+    c1 = wf.float().sum(1)
+    bf = bias + W @ beta
+    o = torch.full((B, L, C), float("nan"), dtype=torch.float16, device="cuda")
+    xd, wd, cd, bd = x.to(torch.float16).cuda(), wf.cuda(), c1.cuda(), bf.cuda()
+    N.check(N.lib().b2d_op_attn_block(xd.data_ptr(), wd.data_ptr(), cd.data_ptr(), bd.data_ptr(), o.data_ptr(), B, L, C, heads,
+                                      G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(o.float().cpu(), ref) < 4e-3     # fp16 weights, Q/K/V and P rounded to fp16
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 512), (3, 1024, 64), (1, 16384, 64), (4, 4, 256)])
 def test_instance_norm_with_skip_and_vector(shape):
     B, HW, C = shape
