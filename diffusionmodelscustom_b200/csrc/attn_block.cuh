@@ -1,6 +1,6 @@
 // Fused low-resolution self-attention: LayerNorm + QKV projection + softmax(QK^T)V for the levels with L = H*W <= 64 tokens
 // (ImageSelfAttention at 8x8, 4x4, 2x2, 1x1: modules_DANRA_conditional.py:91-110; unet_ms.py:6-27), one launch instead of
-// LayerNorm / QKV GEMM / attention.  The out-projection (+ residual) stays on conv_tc.
+// LayerNorm / QKV GEMM / attention / out-projection.
 //
 // CTA = (tile of 128 consecutive tokens = 128/L whole samples, one head).  All MMAs are tcgen05 with accumulators in TMEM:
 //   1. QKV_h = x W'_h^T over K = C in 64-wide k-blocks (TMA ring; A = raw activations, B = the head's D rows of the
@@ -10,7 +10,10 @@
 //      K-major operands, V is written TRANSPOSED ([D][128 keys]) so that it is a K-major B operand for P.V.
 //   3. S = Q K^T for the whole tile (128 x 128); each row only uses the L columns of its own sample (block-diagonal mask),
 //      softmax in registers, P (fp16, zero outside the sample) goes back to TMEM and is the A operand of O = P V.
-//   4. O / rowsum -> fp16 -> global [rows][C] at the head's columns.
+//   4. O / rowsum -> fp16.  Without the fused out-projection it is stored to global [rows][C] at the head's columns.  With it
+//      (the CTAs of a tile's heads form a (1, heads, 1) cluster) O_h becomes the A operand of out_h = O_h Wo[:, hD:(h+1)D]^T
+//      (128 x C, fp32 in TMEM); the per-head partials meet in an L2 workspace, and after a cluster barrier CTA r finalises
+//      128/heads rows: sum over heads in fixed order + bias + residual (+ ReLU) -> fp16.
 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: statistics / read-out / softmax (two warps per TMEM
 // lane quarter, splitting the columns).
 #pragma once
@@ -27,7 +30,7 @@ __host__ __device__ constexpr int ab_stage_bytes() { return CONV_A_BYTES + 3 * D
 template <int D>
 __host__ __device__ constexpr int ab_dpad() { return D < 64 ? 64 : D; }
 template <int D>
-__host__ __device__ constexpr int ab_smem_bytes() { return 1024 + ab_stages<D>() * ab_stage_bytes<D>() + 3 * D * 8 + 128 * 16 + 128 * 4 + 256; }
+__host__ __device__ constexpr int ab_smem_bytes() { return 1024 + ab_stages<D>() * ab_stage_bytes<D>() + 3 * D * 8 + 128 * 16 + 128 * 4 + 384; }
 
 struct AttnBlockParams {
     const float* c1;     // [3C] column sums of the gamma-folded weights
@@ -35,11 +38,19 @@ struct AttnBlockParams {
     f16* out;            // [M][C] attention output (before the out-projection)
     int M, C, L;
     float scale_log2e;
+    // fused out-projection (fuse_out != 0)
+    int fuse_out;
+    const float* out_bias;   // [C]
+    const f16* residual;     // [M][C] (the block input)
+    f16* out_final;          // [M][C]
+    float* ws;               // [tiles][heads][128][C] fp32 partials
+    int final_act;           // 0 none, 1 ReLU
 };
 
 template <int D>
 __global__ void __launch_bounds__(AB_THREADS, 1)
-    attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AttnBlockParams p) {
+    attn_block_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmW, const AttnBlockParams p) {
     pdl_launch_dependents();
     constexpr int STAGES = ab_stages<D>();
     constexpr int SB = ab_stage_bytes<D>();
@@ -65,7 +76,18 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     uint64_t* s_full = accum_full + 2;
     uint64_t* p_ready = accum_full + 3;
     uint64_t* o_full = accum_full + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 5);
+    uint64_t* w_full = accum_full + 5;    // [2] out-projection weight halves
+    uint64_t* o_ready = accum_full + 7;
+    uint64_t* out_full = accum_full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 9);
+    // out-projection weights: Wo[:, head*D .. +DPAD) as DPAD/64 K-atoms of [NW rows][128 B], in halves of NW <= 256 output channels
+    constexpr int OPER_BYTES = 2 * (DPAD / 64) * CONV_A_BYTES + 2 * D * 128;
+    const int NW = p.C > 256 ? 256 : p.C;
+    const int nhalf = p.C > 256 ? 2 : 1;
+    const int hbytes = (DPAD / 64) * NW * 128;
+    uint8_t* sW0 = ring + OPER_BYTES;
+    const bool w1_early = STAGES * SB - OPER_BYTES >= 2 * hbytes;
+    uint8_t* sW1 = w1_early ? sW0 + hbytes : sK;       // late variant: over K / V^T once P.V has retired
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -80,6 +102,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (p.fuse_out) tma_prefetch_desc(&tmW);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -92,6 +115,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             mbar_init(s_full, 1);
             mbar_init(p_ready, 4);
             mbar_init(o_full, 1);
+            mbar_init(&w_full[0], 1);
+            mbar_init(&w_full[1], 1);
+            mbar_init(o_ready, 8);
+            mbar_init(out_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -112,6 +139,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                 mbar_arrive_expect_tx(&full[st], SB);
                 tma_load_2d(ring + st * SB, &tmA, &full[st], kb * 64, m0);
                 tma_load_3d(ring + st * SB + CONV_A_BYTES, &tmB, &full[st], kb * 64, head * D, 0);
+            }
+            if (p.fuse_out) {
+                mbar_wait(accum_full, 0);                      // the ring is drained: its tail is free for Wo
+                for (int hh = 0; hh < nhalf; ++hh) {
+                    if (hh == 1 && !w1_early) mbar_wait(o_full, 0);
+                    uint8_t* dst = hh == 0 ? sW0 : sW1;
+                    mbar_arrive_expect_tx(&w_full[hh], (uint32_t)hbytes);
+                    for (int a = 0; a < DPAD / 64; ++a) tma_load_2d(dst + a * NW * 128, &tmW, &w_full[hh], head * D + a * 64, hh * NW);
+                }
             }
         }
         __syncwarp();
@@ -159,6 +195,24 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                 umma_f16_ts(tmem + O_COL, tmem + P_COL + kk * 8, dv, idesc_o, kk != 0);
             }
             umma_commit(o_full);
+            // ---- out_h = O_h Wo_h^T
+            if (p.fuse_out) {
+                mbar_wait(o_ready, 0);
+                tc_fence_after();
+                const uint32_t idesc_w = umma_idesc_f16(128, NW);
+                for (int hh = 0; hh < nhalf; ++hh) {
+                    mbar_wait(&w_full[hh], 0);
+                    tc_fence_after();
+                    const uint8_t* wb = hh == 0 ? sW0 : sW1;
+#pragma unroll
+                    for (int kk = 0; kk < DPAD / 16; ++kk) {
+                        const uint64_t da = umma_desc_sw128(smem_u32(sQ + (kk >> 2) * CONV_A_BYTES)) + (uint64_t)((kk & 3) * 2);
+                        const uint64_t dw = umma_desc_sw128(smem_u32(wb + (kk >> 2) * NW * 128)) + (uint64_t)((kk & 3) * 2);
+                        umma_f16(tmem + hh * 256, da, dw, idesc_w, kk != 0);
+                    }
+                }
+                umma_commit(out_full);
+            }
         }
         __syncwarp();
     } else {
@@ -311,7 +365,20 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             uint32_t v[32];
             tmem_ld32(tmem + lane_off + (uint32_t)(O_COL + c * 32), v);
             tmem_ld_wait();
-            if (grow < p.M) {
+            if (p.fuse_out) {
+                // O_h -> A operand (K-major, 128B swizzle) over the Q tile; padding columns keep Q's zeros
+                uint8_t* base = sQ + ((c * 32) >> 6) * CONV_A_BYTES + row * 128;
+                const int ch0 = ((c * 32) & 63) >> 3;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 o;
+                    o.x = pack_h2(__uint_as_float(v[j * 8 + 0]) * inv, __uint_as_float(v[j * 8 + 1]) * inv);
+                    o.y = pack_h2(__uint_as_float(v[j * 8 + 2]) * inv, __uint_as_float(v[j * 8 + 3]) * inv);
+                    o.z = pack_h2(__uint_as_float(v[j * 8 + 4]) * inv, __uint_as_float(v[j * 8 + 5]) * inv);
+                    o.w = pack_h2(__uint_as_float(v[j * 8 + 6]) * inv, __uint_as_float(v[j * 8 + 7]) * inv);
+                    *reinterpret_cast<uint4*>(base + (((ch0 + j) ^ sw) << 4)) = o;
+                }
+            } else if (grow < p.M) {
                 uint4* op = reinterpret_cast<uint4*>(p.out + (size_t)grow * p.C + head * D + c * 32);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -324,6 +391,82 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                 }
             }
         }
+        if (p.fuse_out) {
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_ready);
+            // ---- 5. this head's partial of the out-projection -> L2 workspace
+            mbar_wait(out_full, 0);
+            tc_fence_after();
+            float* wrow = p.ws + (((size_t)blockIdx.x * gridDim.y + head) * 128 + row) * p.C;
+            const int nch = p.C >> 5;
+#pragma unroll 1
+            for (int c = hf; c < nch; c += 2) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_off + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    __stcg(reinterpret_cast<float4*>(wrow + c * 32 + j),
+                           make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3])));
+            }
+        }
+    }
+    if (p.fuse_out) {
+        // every head of the tile has written its partial; CTA `head` finalises 128/heads rows in fixed head order
+        __threadfence();
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        if (warp >= 2) {
+            const int et = threadIdx.x - 64;                        // 0..255
+            const int heads = gridDim.y;
+            const int rows_per = 128 / heads;
+            const int c8n = p.C >> 3;
+            const float* wtile = p.ws + (size_t)blockIdx.x * heads * 128 * p.C;
+            for (int it = et; it < rows_per * c8n; it += 256) {
+                const int row = head * rows_per + it / c8n;
+                const int c8 = (it % c8n) * 8;
+                const int grow = m0 + row;
+                if (grow >= p.M) continue;
+                float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                float4 pa[8], pb[8];                                  // all heads' partials in flight at once
+#pragma unroll
+                for (int hh = 0; hh < 8; ++hh) {
+                    if (hh < heads) {
+                        const float4* src = reinterpret_cast<const float4*>(wtile + ((size_t)hh * 128 + row) * p.C + c8);
+                        pa[hh] = __ldcg(src);
+                        pb[hh] = __ldcg(src + 1);
+                    }
+                }
+#pragma unroll
+                for (int hh = 0; hh < 8; ++hh) {
+                    if (hh < heads) {
+                        f[0] += pa[hh].x; f[1] += pa[hh].y; f[2] += pa[hh].z; f[3] += pa[hh].w;
+                        f[4] += pb[hh].x; f[5] += pb[hh].y; f[6] += pb[hh].z; f[7] += pb[hh].w;
+                    }
+                }
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.out_bias + c8));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.out_bias + c8 + 4));
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                const uint4 r4 = *reinterpret_cast<const uint4*>(p.residual + (size_t)grow * p.C + c8);
+                float2 t;
+                t = unpack_h2(r4.x); f[0] += t.x; f[1] += t.y;
+                t = unpack_h2(r4.y); f[2] += t.x; f[3] += t.y;
+                t = unpack_h2(r4.z); f[4] += t.x; f[5] += t.y;
+                t = unpack_h2(r4.w); f[6] += t.x; f[7] += t.y;
+                if (p.final_act == 1) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                uint4 o;
+                o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
+                o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+                *reinterpret_cast<uint4*>(p.out_final + (size_t)grow * p.C + c8) = o;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -334,7 +477,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 }
 
 struct AttnBlockPlan {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmW;
     AttnBlockParams p;
     int D = 0, heads = 0;
 };
@@ -361,6 +504,23 @@ inline int attn_block_plan_build(AttnBlockPlan& pl, const f16* x, const f16* w, 
     uint64_t bs[2] = {(uint64_t)C * 2, (uint64_t)C * C * 2};
     uint32_t bb[3] = {64, (uint32_t)pl.D, 3};
     B2D_TRY(make_tmap_f16(&pl.tmB, w, 3, bd, bs, bb));
+    pl.tmW = pl.tmA;
+    pl.p.fuse_out = 0;
+    return 0;
+}
+
+// Adds the fused out-projection: wo = out_proj.weight [C][C] fp16 (K-major), ws = fp32 workspace of attn_block_ws_floats().
+inline size_t attn_block_ws_floats(int M, int C, int heads) { return (size_t)((M + 127) / 128) * heads * 128 * C; }
+inline bool attn_block_out_supported(int C, int heads) { return heads <= 8 && (128 % heads) == 0 && C <= 512 && (C <= 256 || C == 512); }
+inline int attn_block_plan_fuse_out(AttnBlockPlan& pl, const f16* wo, const float* out_bias, const f16* residual, f16* out_final,
+                                    float* ws, int final_act) {
+    const int C = pl.p.C;
+    uint64_t wd[2] = {(uint64_t)C, (uint64_t)C};
+    uint64_t wsb[1] = {(uint64_t)C * 2};
+    uint32_t wb[2] = {64, (uint32_t)(C > 256 ? 256 : C)};
+    B2D_TRY(make_tmap_f16(&pl.tmW, wo, 2, wd, wsb, wb));
+    pl.p.fuse_out = 1;
+    pl.p.out_bias = out_bias; pl.p.residual = residual; pl.p.out_final = out_final; pl.p.ws = ws; pl.p.final_act = final_act;
     return 0;
 }
 
@@ -371,15 +531,30 @@ inline int attn_block_init_attrs() {
     return 0;
 }
 
-inline int attn_block_launch(const AttnBlockPlan& pl, cudaStream_t st) {
-    const dim3 grid((pl.p.M + 127) / 128, pl.heads);
-    if (pl.D == 32)
-        B2D_CUDA(launch_k(attn_block_kernel<32>, grid, dim3(AB_THREADS), ab_smem_bytes<32>(), st, pl.tmA, pl.tmB, pl.p));
-    else if (pl.D == 64)
-        B2D_CUDA(launch_k(attn_block_kernel<64>, grid, dim3(AB_THREADS), ab_smem_bytes<64>(), st, pl.tmA, pl.tmB, pl.p));
-    else
-        B2D_CUDA(launch_k(attn_block_kernel<128>, grid, dim3(AB_THREADS), ab_smem_bytes<128>(), st, pl.tmA, pl.tmB, pl.p));
+template <int D>
+inline int attn_block_launch_t(const AttnBlockPlan& pl, cudaStream_t st) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((pl.p.M + 127) / 128, pl.heads);
+    cfg.blockDim = dim3(AB_THREADS);
+    cfg.dynamicSmemBytes = ab_smem_bytes<D>();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = pl.p.fuse_out ? pl.heads : 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = g_pdl_enabled;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    B2D_CUDA(cudaLaunchKernelEx(&cfg, attn_block_kernel<D>, pl.tmA, pl.tmB, pl.tmW, pl.p));
     return 0;
+}
+
+inline int attn_block_launch(const AttnBlockPlan& pl, cudaStream_t st) {
+    if (pl.D == 32) return attn_block_launch_t<32>(pl, st);
+    if (pl.D == 64) return attn_block_launch_t<64>(pl, st);
+    return attn_block_launch_t<128>(pl, st);
 }
 
 }  // namespace b2d

@@ -502,11 +502,24 @@ struct Builder {
         // low-resolution levels (L <= 64 tokens): LayerNorm + QKV + attention in ONE launch
         static const bool no_attn_block = getenv("B2D_NO_ATTN_BLOCK") != nullptr;
         const bool fused_block = !no_attn_block && !h->cfg.debug_simt_conv && attn_block_supported(L, C, heads);
+        bool fused_out = false;
         if (fused_block) {
             auto pl = std::make_shared<AttnBlockPlan>();
             if (attn_block_plan_build(*pl, x, W<f16>(role + ".qkvln.w"), W<float>(role + ".qkvln.c1"), W<float>(role + ".qkvln.b"), ao,
                                       rows, C, L, heads) != 0) { err = -1; return; }
-            ops.meta(role + ".attn", "attn_block", 6.0 * rows * C * C + 4.0 * (double)L * L * C * B, 4.0 * rows * C + 6.0 * C * C);
+            static const bool no_out_fuse = getenv("B2D_NO_ATTN_OUT_FUSE") != nullptr;
+            static const int out_fuse_maxc = getenv("B2D_ATTN_OUT_FUSE_MAXC") ? atoi(getenv("B2D_ATTN_OUT_FUSE_MAXC")) : 128;
+            fused_out = !no_out_fuse && attn_block_out_supported(C, heads) && C <= out_fuse_maxc;
+            double fl = 6.0 * rows * C * C + 4.0 * (double)L * L * C * B, by = 4.0 * rows * C + 6.0 * C * C;
+            if (fused_out) {   // + out-projection, bias, residual (and the decoder's ReLU): the whole block is one launch
+                float* ws = nullptr;
+                if (h->alloc(&ws, attn_block_ws_floats(rows, C, heads)) != 0) { err = -2; return; }
+                if (attn_block_plan_fuse_out(*pl, W<f16>(role + ".out.w"), W<float>(role + ".out.b"), x,
+                                             h->cfg.attn_ff ? s_mid : out, ws, h->cfg.attn_ff ? 0 : final_act) != 0) { err = -1; return; }
+                fl += 2.0 * rows * C * C;
+                by += 4.0 * rows * C + 2.0 * C * C;
+            }
+            ops.meta(role + ".attn", "attn_block", fl, by);
             ops.push_back([=](cudaStream_t st) { return attn_block_launch(*pl, st); });
         } else if (fold) {
             next_ln_c1 = W<float>(role + ".qkvln.c1");
@@ -529,11 +542,11 @@ struct Builder {
             ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
         }
         if (!h->cfg.attn_ff) {
-            conv(ao, hw, hw, C, out, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, final_act);
+            if (!fused_out) conv(ao, hw, hw, C, out, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, final_act);
         } else {
             f16* mid = s_mid;
             f16* h1 = s_h1;
-            conv(ao, hw, hw, C, mid, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, 0);
+            if (!fused_out) conv(ao, hw, hw, C, mid, C, 1, 1, 0, false, role + ".out", x, nullptr, 0, 0);
             const float* g2 = W<float>(role + ".ffln.g");
             const float* b2 = W<float>(role + ".ffln.b");
             if (fold) {
@@ -1452,6 +1465,22 @@ int b2d_op_attn_block(const void* x, const void* w_folded, const float* c1, cons
     AttnBlockPlan pl;
     B2D_TRY(attn_block_plan_build(pl, (const f16*)x, (const f16*)w_folded, c1, bias, (f16*)o, B * L, C, L, heads));
     return attn_block_launch(pl, as_stream(stream));
+}
+
+int b2d_op_attn_block_out(const void* x, const void* w_folded, const float* c1, const float* bias, const void* wo,
+                          const float* out_bias, void* y, int32_t B, int32_t L, int32_t C, int32_t heads, int32_t final_act,
+                          void* stream) {
+    B2D_CHECK(attn_block_supported(L, C, heads) && attn_block_out_supported(C, heads), "shape not eligible for the fused attention block");
+    B2D_TRY(attn_block_init_attrs());
+    AttnBlockPlan pl;
+    B2D_TRY(attn_block_plan_build(pl, (const f16*)x, (const f16*)w_folded, c1, bias, nullptr, B * L, C, L, heads));
+    float* ws = nullptr;
+    B2D_CUDA(cudaMalloc(&ws, attn_block_ws_floats(B * L, C, heads) * sizeof(float)));
+    int rc = attn_block_plan_fuse_out(pl, (const f16*)wo, out_bias, (const f16*)x, (f16*)y, ws, final_act);
+    if (rc == 0) rc = attn_block_launch(pl, as_stream(stream));
+    cudaStreamSynchronize(as_stream(stream));
+    cudaFree(ws);
+    return rc;
 }
 
 int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t vec_stride, void* y, float* stats_ws,

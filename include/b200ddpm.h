@@ -128,6 +128,11 @@ int b2d_op_attention(const void* qkv_f16, void* o_f16, int32_t B, int32_t L, int
  * (modules_DANRA_conditional.py:100-107); the out-projection is a b2d_op_conv2d. */
 int b2d_op_attn_block(const void* x_f16, const void* w_folded_f16, const float* c1, const float* bias, void* o_f16,
                       int32_t B, int32_t L, int32_t C, int32_t heads, void* stream);
+/* The whole ImageSelfAttention block in one launch: y = act( out_proj( MHA_core( LN(x) ) ) + x ) (modules_DANRA_conditional.py:91-110).
+ * wo: out_proj.weight f16 [C][C]; final_act 0 none / 1 ReLU (DecoderBlock, :459). heads <= 8. */
+int b2d_op_attn_block_out(const void* x_f16, const void* w_folded_f16, const float* c1, const float* bias, const void* wo_f16,
+                          const float* out_bias, void* y_f16, int32_t B, int32_t L, int32_t C, int32_t heads,
+                          int32_t final_act, void* stream);
 int b2d_op_instnorm(const void* x_f16, const void* skip_f16, const float* vec, int32_t vec_stride, void* y_f16,
                     float* stats_ws, int32_t B, int32_t HW, int32_t C, void* stream);
 int b2d_op_posterior_update(float* x, const float* eps, const float* z_or_null, const float* betas, const float* alphas,

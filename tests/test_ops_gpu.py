@@ -170,6 +170,40 @@ def test_fused_lowres_attention_block(case):
     assert G.rel_l2(o.float().cpu(), ref) < 4e-3     # fp16 weights, Q/K/V and P rounded to fp16
 
 
+ATTN_BLOCK_OUT_CASES = [(64, 64, 128, 4, 0), (64, 16, 256, 4, 1), (64, 4, 512, 4, 0), (5, 4, 512, 4, 1), (3, 64, 128, 4, 1),
+                        (7, 1, 512, 4, 0), (4, 16, 256, 8, 0), (2, 64, 256, 8, 1), (9, 2, 128, 4, 0), (3, 32, 512, 8, 1)]
+
+
+@pytest.mark.parametrize("case", ATTN_BLOCK_OUT_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}_act{a}" for b, l, c, h, a in ATTN_BLOCK_OUT_CASES])
+def test_fused_lowres_attention_block_with_out_projection(case):
+    """The whole ImageSelfAttention block (LN, MHA incl. out_proj, + x, optional ReLU) in one launch vs nn.MultiheadAttention."""
+    B, L, C, heads, act = case
+    g = torch.Generator().manual_seed(11 * L + C + heads)
+    x = _bf(torch.randn(B, L, C, generator=g) * 1.7 + 0.4)
+    gamma, beta = 1 + 0.3 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    mha = torch.nn.MultiheadAttention(C, heads, batch_first=True)
+    with torch.no_grad():
+        mha.in_proj_weight.copy_(torch.randn(3 * C, C, generator=g) / math.sqrt(C))
+        mha.in_proj_bias.copy_(0.1 * torch.randn(3 * C, generator=g))
+        mha.out_proj.weight.copy_(_bf(torch.randn(C, C, generator=g) / math.sqrt(C)))
+        mha.out_proj.bias.copy_(0.1 * torch.randn(C, generator=g))
+        xn = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+        ref = mha(xn, xn, xn)[0] + x
+        if act:
+            ref = torch.relu(ref)
+    W, bias = mha.in_proj_weight.detach(), mha.in_proj_bias.detach()
+    wf = (W * gamma[None, :]).to(torch.float16)
+    c1 = wf.float().sum(1)
+    bf = bias + W @ beta
+    y = torch.full((B, L, C), float("nan"), dtype=torch.float16, device="cuda")
+    xd, wd, cd, bd = x.to(torch.float16).cuda(), wf.cuda(), c1.cuda(), bf.cuda()
+    wo, bo = mha.out_proj.weight.detach().to(torch.float16).cuda(), mha.out_proj.bias.detach().cuda()
+    N.check(N.lib().b2d_op_attn_block_out(xd.data_ptr(), wd.data_ptr(), cd.data_ptr(), bd.data_ptr(), wo.data_ptr(), bo.data_ptr(),
+                                          y.data_ptr(), B, L, C, heads, act, G.stream()))
+    torch.cuda.synchronize()
+    assert G.rel_l2(y.float().cpu(), ref) < 4e-3
+
+
 @pytest.mark.parametrize("shape", [(2, 16, 512), (3, 1024, 64), (1, 16384, 64), (4, 4, 256)])
 def test_instance_norm_with_skip_and_vector(shape):
     B, HW, C = shape
