@@ -397,11 +397,21 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                 const int row = split * rows_per + it / (BN / 8);
                 const int c8 = (it % (BN / 8)) * 8;
                 float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (int sp = 0; sp < p.splits; ++sp) {
-                    const float4* src = reinterpret_cast<const float4*>(wtile + ((size_t)sp * 128 + row) * BN + c8);
-                    const float4 a = __ldcg(src), b = __ldcg(src + 1);
-                    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w;
-                    f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+                float4 pa[8], pb[8];      // every split's partial in flight at once (one L2 round trip, not `splits`), summed in split order
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                    if (sp < p.splits) {
+                        const float4* src = reinterpret_cast<const float4*>(wtile + ((size_t)sp * 128 + row) * BN + c8);
+                        pa[sp] = __ldcg(src);
+                        pb[sp] = __ldcg(src + 1);
+                    }
+                }
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                    if (sp < p.splits) {
+                        f[0] += pa[sp].x; f[1] += pa[sp].y; f[2] += pa[sp].z; f[3] += pa[sp].w;
+                        f[4] += pb[sp].x; f[5] += pb[sp].y; f[6] += pb[sp].z; f[7] += pb[sp].w;
+                    }
                 }
                 const int lw = row % p.TW;
                 const int lh = (row / p.TW) % p.TH;
