@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     }
     if (p.fuse_out) {
         // every head of the tile has written its partial; CTA `head` finalises 128/heads rows in fixed head order
-        __threadfence();
+        // barrier.cluster arrive.release / wait.acquire order the partial-tile writes (st.global.cg) before the peers' ld.global.cg
         cluster_arrive_release();
         cluster_wait_acquire();
         if (warp >= 2) {

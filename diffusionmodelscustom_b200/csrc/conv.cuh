@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
     }
     if (p.splits > 1) {
         // all CTAs of the cluster have written their partial tiles; each finalises 128/splits rows in fixed split order
-        __threadfence();
+        // barrier.cluster arrive.release / wait.acquire order the partial-tile writes (st.global.cg) before the peers' ld.global.cg
         cluster_arrive_release();
         cluster_wait_acquire();
         if (warp >= 2) {

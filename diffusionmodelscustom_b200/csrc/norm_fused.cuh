@@ -89,8 +89,12 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
     cluster_wait_acquire();
     if (threadIdx.x < 128) {
         const int k = threadIdx.x >> 6, c = threadIdx.x & 63;
+        float pv[8];                                              // all ranks' partials in flight at once, summed in rank order
+#pragma unroll
+        for (int r = 0; r < 8; ++r) pv[r] = (r < csize) ? ld_dsmem_f32(&s_part[k][c], r) : 0.f;
         float s = 0.f;
-        for (int r = 0; r < csize; ++r) s += ld_dsmem_f32(&s_part[k][c], r);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += pv[r];
         s_red[0][k][c] = s;
     }
     __syncthreads();
