@@ -45,7 +45,7 @@ WORKLOADS = {
 
 # DRAM bytes per launch (dram__bytes via ncu, cold-cache, averaged over the launches of the class) for the cfg2 step at batch 64:
 # profiles/r1_ncu_step_cfg2_b64_final_sections.txt.  Reported as roofline.traffic for that workload only.
-NCU_TRAFFIC_CFG2 = {"conv_tc": 2.75e6, "attn_tc": 16.81e6, "gemm_stream": 7.89e6, "norm_fused": 5.01e6, "layernorm": 0.69e6,
+NCU_TRAFFIC_CFG2 = {"conv_tc": 2.91e6, "attn_tc": 15.76e6, "gemm_stream": 7.42e6, "norm_fused": 5.01e6, "attn_block": 1.28e6,
                     "tail_conv": 33.6e6, "stem_conv": 17.9e6, "plane_stats": 33.6e6, "temb_project": 1.65e6}
 
 
