@@ -91,6 +91,14 @@ __device__ __forceinline__ void conv_epilogue8(const ConvParams& p, float (&f)[8
 
 __device__ __forceinline__ void cluster_arrive_release() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait_acquire() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// 16-byte load from the shared memory of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ float4 ld_dsmem_f4(const void* local_ptr, int rank) {
+    uint32_t a = smem_u32(local_ptr), ra;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra));
+    return v;
+}
 
 // ------------------------------------------------------------------------------------------------ tcgen05 path
 constexpr int CONV_TC_THREADS = 192;  // warp0 TMA, warp1 MMA(+TMEM alloc), warps2-5 epilogue
@@ -270,6 +278,21 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
         mbar_wait(accum_full, 0);
         tc_fence_after();
         if (p.splits > 1) {
+            if (p.ws == nullptr) {
+                // raw fp32 partial tile -> this CTA's own (drained) pipeline memory, read by the cluster peers through DSMEM;
+                // 16-byte chunks XOR-swizzled by the row so that a warp's 32 rows hit all banks
+                float4* prow = reinterpret_cast<float4*>(sA) + (size_t)row * (BN / 4);
+#pragma unroll 1
+                for (int ch = 0; ch < BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        prow[(ch * 8 + j) ^ (row & 7)] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+            } else {
             // raw fp32 partial tile -> workspace (this thread's row: BN contiguous floats)
             const size_t tile_id = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
             float* wrow = p.ws + ((tile_id * p.splits + split) * 128 + row) * BN;
@@ -283,6 +306,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                     __stcg(reinterpret_cast<float4*>(wrow + ch * 32 + j),
                            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                        __uint_as_float(v[j + 3])));
+            }
             }
         } else {
             // Coalesced epilogue: each thread (= output pixel) builds its 128-byte row of a 64-channel block in a
@@ -398,6 +422,17 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                 const int c8 = (it % (BN / 8)) * 8;
                 float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 float4 pa[8], pb[8];      // every split's partial in flight at once (one L2 round trip, not `splits`), summed in split order
+                if (p.ws == nullptr) {
+                    const float4* prow = reinterpret_cast<const float4*>(sA) + (size_t)row * (BN / 4);
+                    const int jc = c8 >> 2;
+#pragma unroll
+                    for (int sp = 0; sp < 8; ++sp) {
+                        if (sp < p.splits) {
+                            pa[sp] = ld_dsmem_f4(prow + (jc ^ (row & 7)), sp);
+                            pb[sp] = ld_dsmem_f4(prow + ((jc + 1) ^ (row & 7)), sp);
+                        }
+                    }
+                } else {
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) {
                     if (sp < p.splits) {
@@ -405,6 +440,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                         pa[sp] = __ldcg(src);
                         pb[sp] = __ldcg(src + 1);
                     }
+                }
                 }
 #pragma unroll
                 for (int sp = 0; sp < 8; ++sp) {
@@ -430,6 +466,10 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                 }
                 conv_epilogue8(p, f, n, pix * (size_t)p.CoutT + cbase + c8, cbase + c8);
             }
+        }
+        if (p.ws == nullptr) {   // no CTA may exit (and release its shared memory) while a peer can still read its partial tile
+            cluster_arrive_release();
+            cluster_wait_acquire();
         }
     }
     tc_fence_before();
@@ -564,11 +604,14 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     int splits = 1;
     while (splits < 8 && tiles * splits * 2 <= num_sms && total_kb / (splits * 2) >= 4) splits *= 2;
     p.splits = splits;
-    pl.ws_floats = splits > 1 ? (size_t)tiles * splits * 128 * bn : 0;
+    static const bool splitk_l2 = getenv("B2D_SPLITK_L2") != nullptr;
+    pl.ws_floats = (splits > 1 && splitk_l2) ? (size_t)tiles * splits * 128 * bn : 0;
     // deep pipelines for deep-K problems that leave SMs to spare anyway (the TMA round trip paces them)
     const int kb_cta = total_kb / splits;
     const bool deep = tiles * splits <= num_sms && (splits == 1 ? kb_cta >= 6 : kb_cta >= 12);   // measured: 8-stage CTAs in
     pl.stages = (bn == 64) ? (deep ? 8 : 4) : (deep ? 6 : 3);                                     // 8-CTA clusters schedule worse
+    static const bool shallow_only = getenv("B2D_CONV_SHALLOW") != nullptr;                       // A/B: always the small rings
+    if (shallow_only) pl.stages = (bn == 64) ? 4 : 3;
     pl.grid = dim3(mtiles, p.Cout / bn, splits);
     const uint64_t C = p.Cin, W = p.Wi, H = p.Hi, B = p.B;
     if (p.stride == 1) {
@@ -644,7 +687,7 @@ inline int conv_tc_launch_t(const ConvPlan& pl, cudaStream_t st) {
 
 inline int conv_launch_tc(const ConvPlan& pl, cudaStream_t st) {
     B2D_CHECK(pl.tc_ready, "conv plan not built");
-    B2D_CHECK(pl.p.splits == 1 || pl.p.ws != nullptr, "split-K plan without workspace");
+    // split-K partial tiles: through DSMEM (p.ws == nullptr) or through an L2 workspace (p.ws set: B2D_SPLITK_L2 A/B switch)
     if (pl.bn == 64) return pl.stages == 8 ? conv_tc_launch_t<64, 8>(pl, st) : conv_tc_launch_t<64, 4>(pl, st);
     return pl.stages == 6 ? conv_tc_launch_t<128, 6>(pl, st) : conv_tc_launch_t<128, 3>(pl, st);
 }
