@@ -62,6 +62,19 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
         cp_async16(tile + (size_t)r * 128 + c * 16, p.x + base + (size_t)(r0 + r) * row_pitch + c * 8, true);
     }
     cp_async_commit();
+    // operands of the apply phase that do not depend on the statistics are fetched now, under the reduction's latency:
+    // the per-sample vector (MODE 0) and, when a thread owns at most 4 items, its share of the skip tensor
+    __shared__ float s_vec[64];
+    if (MODE == 0 && threadIdx.x < 64) s_vec[threadIdx.x] = p.vec ? p.vec[(size_t)b * p.vec_stride + grp * 64 + threadIdx.x] : 0.f;
+    const bool pre_add = p.add != nullptr && nrows * 8 <= 4 * 256;
+    uint4 addv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        addv[k] = make_uint4(0, 0, 0, 0);
+        const int i = threadIdx.x + k * 256;
+        if (pre_add && i < nrows * 8)
+            addv[k] = *reinterpret_cast<const uint4*>(p.add + base + (size_t)(r0 + (i >> 3)) * row_pitch + (i & 7) * 8);
+    }
     cp_async_wait<0>();
     __syncthreads();
     // ---- partial statistics (per channel of the 64-wide row; MODE 1 folds the 64 columns afterwards)
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
     // no CTA may exit (and release its shared memory) while a peer can still read its partials
     cluster_arrive_release();
     // ---- apply from shared memory
-    for (int i = threadIdx.x; i < nrows * 8; i += 256) {
+    for (int i = threadIdx.x, k = 0; i < nrows * 8; i += 256, ++k) {
         const int r = i >> 3, c8 = (i & 7) * 8;
         const uint4 xv = *reinterpret_cast<const uint4*>(tile + (size_t)r * 128 + c8 * 2);
         const size_t e = base + (size_t)(r0 + r) * row_pitch + c8;
@@ -147,7 +160,9 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
             for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
         }
         if (p.add) {
-            const uint4 av = *reinterpret_cast<const uint4*>(p.add + e);
+            uint4 av;
+            if (pre_add) av = (k == 0) ? addv[0] : (k == 1) ? addv[1] : (k == 2) ? addv[2] : addv[3];
+            else av = *reinterpret_cast<const uint4*>(p.add + e);
             t = unpack_h2(av.x); f[0] += t.x; f[1] += t.y;
             t = unpack_h2(av.y); f[2] += t.x; f[3] += t.y;
             t = unpack_h2(av.z); f[4] += t.x; f[5] += t.y;
@@ -158,9 +173,14 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
             for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
         }
         if (p.vec) {
-            const float* vp = p.vec + (size_t)b * p.vec_stride + ch;
+            if (MODE == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += vp[j];
+                for (int j = 0; j < 8; ++j) f[j] += s_vec[c8 + j];
+            } else {
+                const float* vp = p.vec + (size_t)b * p.vec_stride + ch;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] += vp[j];
+            }
         }
         uint4 o;
         o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
