@@ -94,11 +94,6 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const int m0 = blockIdx.x * 128;
     const int nkb = p.C >> 6;
 
-    for (int i = threadIdx.x; i < 3 * D; i += AB_THREADS) {
-        const int mat = i / D, d = i - mat * D;
-        s_c1[i] = __ldg(p.c1 + mat * p.C + head * D + d);
-        s_bias[i] = __ldg(p.bias + mat * p.C + head * D + d);
-    }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
@@ -221,6 +216,12 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         const int row = q * 32 + lane;
         const int sw = row & 7;
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        // LN column sums / folded bias of this head's 3D columns (visible to all epilogue warps after the statistics barrier)
+        for (int i = threadIdx.x - 64; i < 3 * D; i += 256) {
+            const int mat = i / D, d = i - mat * D;
+            s_c1[i] = __ldg(p.c1 + mat * p.C + head * D + d);
+            s_bias[i] = __ldg(p.bias + mat * p.C + head * D + d);
+        }
         // ---- LayerNorm statistics from the A stages (each half-warp-group sums 4 of the 8 chunks of a 64-channel block)
         float s1 = 0.f, s2 = 0.f;
         for (int kb = 0; kb < nkb; ++kb) {

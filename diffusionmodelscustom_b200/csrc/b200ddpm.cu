@@ -835,7 +835,8 @@ static int init_batch_buffers(Handle* h) {
     const int B = c.max_batch, H = c.img_size;
     B2D_TRY(h->alloc(&h->d_t, B));
     B2D_TRY(h->alloc(&h->d_y, B));
-    B2D_TRY(h->alloc(&h->d_step, 4));
+    B2D_TRY(h->alloc(&h->d_step, 4));   // [0] step index i, [1] arrival counter of the posterior update (self-resetting)
+    B2D_CUDA(cudaMemset(h->d_step, 0, 16));
     B2D_TRY(h->alloc(&h->d_eps, (size_t)B * c.c_out * H * H));
     B2D_TRY(h->alloc(&h->d_stats, STATS_CAPACITY_PER_SAMPLE * (size_t)B));
     h->n_temb = TEMB_R_TOTAL;
@@ -1201,13 +1202,12 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
                 B2D_TRY(run_step_ops(p.ph, st, true));
                 const size_t ni = per_sample * p.Bi;
                 const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
+                B2D_TRY(join_temb_side(p.ph, st));   // the update's last block advances d_t, which the side branch reads
                 B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, xs, p.ph->d_eps,
                                   noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
                                   p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
                                   noise_scale, n));
-                B2D_TRY(join_temb_side(p.ph, st));
-                B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, st, p.ph->d_step, p.ph->d_t, p.Bi));
-                launches += (int64_t)p.ph->step_ops.size() + 2;
+                launches += (int64_t)p.ph->step_ops.size() + 1;
             }
         }
         h->last_launches = launches;
@@ -1234,12 +1234,11 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
                 B2D_TRY(run_step_ops(p.ph, si, true));
                 const size_t ni = per_sample * p.Bi;
                 const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
+                B2D_TRY(join_temb_side(p.ph, si));   // the update's last block advances d_t, which the side branch reads
                 B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, si, xs, p.ph->d_eps,
                                   noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
                                   p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
                                   noise_scale, n));
-                B2D_TRY(join_temb_side(p.ph, si));
-                B2D_CUDA(launch_k(step_advance_kernel, dim3(1), dim3(256), 0, si, p.ph->d_step, p.ph->d_t, p.Bi));
                 if (i > 0) {
                     B2D_CUDA(cudaEventRecord(h->ev_join[i], si));
                     B2D_CUDA(cudaStreamWaitEvent(cs, h->ev_join[i], 0));

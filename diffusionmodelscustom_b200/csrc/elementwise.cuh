@@ -734,8 +734,27 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
         xv.w = __fadd_rn(__fmul_rn(c1, __fsub_rn(xv.w, __fmul_rn(c2, ev.w))), __fmul_rn(c3, zv.w));
         reinterpret_cast<float4*>(x)[v] = xv;
     }
+    // Inside the reverse loop (t_arr != nullptr) the last block to finish advances the device-resident step state for the next
+    // UNet evaluation: i <- i-1, t[b] <- i-1.  Every block read *step_ptr before it arrives, so nobody sees the new value early.
+    // step_ptr[1] is the (self-resetting) arrival counter.
+    if (t_arr != nullptr) {
+        __shared__ bool s_last;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(reinterpret_cast<unsigned int*>(step_ptr + 1), 1u) == gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last) {
+            for (int b = threadIdx.x; b < B; b += blockDim.x) t_arr[b] = i - 1;
+            if (threadIdx.x == 0) {
+                step_ptr[0] = i - 1;
+                step_ptr[1] = 0;
+            }
+        }
+    }
 }
-// Runs after the update (stream order): i <- i-1 and t[b] <- i-1 for the next UNet evaluation.
+// Stand-alone form of the step advance (kept for plain-stream debugging): i <- i-1 and t[b] <- i-1.
 __global__ void step_advance_kernel(int* step_ptr, int* t_arr, int B) {
     pdl_launch_dependents();
     pdl_wait();

@@ -61,12 +61,6 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
     const int num_tiles = (M + 127) / 128;
     __shared__ __align__(16) float2 s_stat[2 * 512];          // per-group partial (sum, sum of squares) of the LN statistics, double-buffered
     __shared__ __align__(16) float s_bias[256], s_c1[256];   // bias / LN column sums of this CTA's N block (persistent => loaded once)
-    for (int i = threadIdx.x; i < NB; i += GS_THREADS) {
-        const int col = nblk * NB + i;
-        const int cb = p.convt ? col % p.CoutT : col;
-        s_bias[i] = p.bias ? __ldg(p.bias + cb) : 0.f;
-        s_c1[i] = p.ln_c1 ? __ldg(p.ln_c1 + cb) : 0.f;
-    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -157,6 +151,15 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
         const int sw = row & 7;
         const bool elected = (warp - 2) == pair * 8 && lane == 0;      // issues this pair's TMA stores
         const int bar_id = 1 + pair;
+        // bias / LN column sums of this CTA's N block: fetched by the epilogue warps only, so the TMA and MMA warps do not wait
+        // for this L2 round trip at the prologue's __syncthreads
+        for (int i = threadIdx.x - 64; i < NB; i += GS_EPI_THREADS) {
+            const int col = nblk * NB + i;
+            const int cb = p.convt ? col % p.CoutT : col;
+            s_bias[i] = p.bias ? __ldg(p.bias + cb) : 0.f;
+            s_c1[i] = p.ln_c1 ? __ldg(p.ln_c1 + cb) : 0.f;
+        }
+        named_bar_sync(4, GS_EPI_THREADS);
         int it = 0, blk = 0;                                   // blk: running 64-column block counter
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
