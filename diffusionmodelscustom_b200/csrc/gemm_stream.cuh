@@ -149,8 +149,12 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
         const int row = q * 32 + lane;
         const int HW = p.Ho * p.Wo;
         const int sw = row & 7;
-        const bool elected = (warp - 2) == pair * 8 && lane == 0;      // issues this pair's TMA stores
-        const int bar_id = 1 + pair;
+        // The two warps that share a TMEM lane quarter inside a pair (low / high 32 columns of the pair's 64-column blocks) form a
+        // sub-group with its own 32-row staging tiles, its own 64-thread named barrier and its own TMA stores: no barrier in
+        // the block loop is wider than two warps.
+        const int sg = pair * 4 + q;                                     // 0..7
+        const bool elected = half == 0 && lane == 0;                    // issues this sub-group's TMA stores
+        const int bar_id = 1 + sg;                                       // named barriers 1..8 (9..12: statistics per quarter, 13: init)
         // bias / LN column sums of this CTA's N block: fetched by the epilogue warps only, so the TMA and MMA warps do not wait
         // for this L2 round trip at the prologue's __syncthreads
         for (int i = threadIdx.x - 64; i < NB; i += GS_EPI_THREADS) {
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
             s_bias[i] = p.bias ? __ldg(p.bias + cb) : 0.f;
             s_c1[i] = p.ln_c1 ? __ldg(p.ln_c1 + cb) : 0.f;
         }
-        named_bar_sync(4, GS_EPI_THREADS);
+        named_bar_sync(13, GS_EPI_THREADS);
         int it = 0, blk = 0;                                   // blk: running 64-column block counter
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                 if (lane == 0) mbar_arrive(&a_empty[st]);
                 float2* sst = s_stat + (it & 1) * 512;
                 sst[grp * 128 + row] = make_float2(s1, s2);
-                named_bar_sync(3, GS_EPI_THREADS);
+                named_bar_sync(9 + q, 128);                    // the four warps that own this lane quarter
                 s1 = 0.f; s2 = 0.f;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {                   // fixed order: every group derives bit-identical statistics
@@ -206,10 +210,10 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
 #pragma unroll 1
             for (int jb = 0; jb < NB / 64; ++jb, ++blk) {
                 if ((blk & 1) != pair) continue;
-                uint8_t* stg = sO + (pair * OBP + ((blk >> 1) % OBP)) * CONV_A_BYTES;
-                uint4* srow = reinterpret_cast<uint4*>(stg + row * 128);
+                uint8_t* stg = sO + (sg * OBP + ((blk >> 1) % OBP)) * (CONV_A_BYTES / 4);   // [32 rows][128 B], 128B swizzle
+                uint4* srow = reinterpret_cast<uint4*>(stg + lane * 128);
                 if (elected) tma_store_wait_read_n<OBP - 1>();   // the store that used this buffer OBP blocks ago has read it
-                named_bar_sync(bar_id, 256);
+                named_bar_sync(bar_id, 64);
                 const int col = nblk * NB + jb * 64;           // GEMM column of this block
                 int cbase = col, ab = 0;
                 if (p.convt) {
@@ -281,13 +285,14 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                     }
                 }
                 fence_proxy_async();
-                named_bar_sync(bar_id, 256);
+                named_bar_sync(bar_id, 64);
                 if (elected) {
+                    const int ms = m0 + q * 32;                 // first GEMM row of this sub-group's 32-row slice
                     if (p.convt) {
-                        const int n0 = m0 / HW, rem = m0 - n0 * HW;
+                        const int n0 = ms / HW, rem = ms - n0 * HW;
                         tma_store_5d(&tmO, stg, (ab & 1) * p.CoutT + cbase, rem % p.Wo, ab >> 1, rem / p.Wo, n0);
                     } else {
-                        tma_store_2d(&tmO, stg, col, m0);
+                        tma_store_2d(&tmO, stg, col, ms);
                     }
                     tma_store_commit();
                 }
@@ -355,13 +360,17 @@ inline int gemm_stream_plan_build(GemmStreamPlan& pl, int num_sms) {
         const uint64_t Co = p.CoutT, Wo = p.Wo, Ho = p.Ho;
         uint64_t dims[5] = {2 * Co, Wo, 2, Ho, (uint64_t)p.B};
         uint64_t str[4] = {2 * Co * 2, 2 * Wo * Co * 2, 4 * Wo * Co * 2, 4 * Ho * Wo * Co * 2};
-        uint32_t box[5] = {64, (uint32_t)TW, 1, (uint32_t)TH, (uint32_t)TN};
+        (void)TN;
+        const int tw = TW < 32 ? TW : 32;                       // 32 consecutive GEMM rows = a (tw, th, tn) box
+        const int th = (32 / tw) < TH ? (32 / tw) : TH;
+        const int tn = 32 / (tw * th);
+        uint32_t box[5] = {64, (uint32_t)tw, 1, (uint32_t)th, (uint32_t)tn};
         B2D_TRY(make_tmap_f16(&pl.tmO, p.out, 5, dims, str, box));
     } else {
         uint64_t od[2] = {(uint64_t)p.Cout, (uint64_t)pl.M};
         uint64_t os[1] = {(uint64_t)p.Cout * 2};
-        uint32_t ob[2] = {64, 128};
-        B2D_TRY(make_tmap_f16(&pl.tmO, p.out, 2, od, os, ob));
+        uint32_t ob[2] = {64, 128}, ob32[2] = {64, 32};
+        B2D_TRY(make_tmap_f16(&pl.tmO, p.out, 2, od, os, ob32));      // stores: 32-row slices (one per epilogue sub-group)
         if (p.residual) B2D_TRY(make_tmap_f16(&pl.tmR, p.residual, 2, od, os, ob));
     }
     if (!p.residual) pl.tmR = pl.tmO;
