@@ -13,7 +13,9 @@
 //   4. O / rowsum -> fp16.  Without the fused out-projection it is stored to global [rows][C] at the head's columns.  With it
 //      (the CTAs of a tile's heads form a (1, heads, 1) cluster) O_h becomes the A operand of out_h = O_h Wo[:, hD:(h+1)D]^T
 //      (128 x C, fp32 in TMEM); the per-head partials meet in an L2 workspace, and after a cluster barrier CTA r finalises
-//      128/heads rows: sum over heads in fixed order + bias + residual (+ ReLU) -> fp16.
+//      128/heads rows: sum over heads in fixed order + bias + residual (+ ReLU) -> fp16.  A second variant (fuse_out == 2) exchanges
+//      the fp16 head outputs instead: every CTA scatters O_h through DSMEM into all peers' gathered [128][C] operand and then
+//      computes its own D output channels over K = C (no fp32 partials, no workspace).
 // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: statistics / read-out / softmax (two warps per TMEM
 // lane quarter, splitting the columns).
 #pragma once
@@ -30,7 +32,7 @@ __host__ __device__ constexpr int ab_stage_bytes() { return CONV_A_BYTES + 3 * D
 template <int D>
 __host__ __device__ constexpr int ab_dpad() { return D < 64 ? 64 : D; }
 template <int D>
-__host__ __device__ constexpr int ab_smem_bytes() { return 1024 + ab_stages<D>() * ab_stage_bytes<D>() + 3 * D * 8 + 128 * 16 + 128 * 4 + 384; }
+__host__ __device__ constexpr int ab_smem_bytes() { return 1024 + ab_stages<D>() * ab_stage_bytes<D>() + 3 * D * 8 + 128 * 16 + 128 * 4 + 512; }
 
 struct AttnBlockParams {
     const float* c1;     // [3C] column sums of the gamma-folded weights
@@ -79,7 +81,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     uint64_t* w_full = accum_full + 5;    // [2] out-projection weight halves
     uint64_t* o_ready = accum_full + 7;
     uint64_t* out_full = accum_full + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 9);
+    uint64_t* w2_full = accum_full + 9;   // [4] gather mode: out_proj weight k-blocks
+    uint64_t* w2_empty = accum_full + 13; // [4]
+    uint64_t* out2_full = accum_full + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 18);
     // out-projection weights: Wo[:, head*D .. +DPAD) as DPAD/64 K-atoms of [NW rows][128 B], in halves of NW <= 256 output channels
     constexpr int OPER_BYTES = 2 * (DPAD / 64) * CONV_A_BYTES + 2 * D * 128;
     const int NW = p.C > 256 ? 256 : p.C;
@@ -88,6 +93,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     uint8_t* sW0 = ring + OPER_BYTES;
     const bool w1_early = STAGES * SB - OPER_BYTES >= 2 * hbytes;
     uint8_t* sW1 = w1_early ? sW0 + hbytes : sK;       // late variant: over K / V^T once P.V has retired
+    // gather mode (fuse_out == 2): every head's O (fp16) is scattered through DSMEM into each CTA's G = [C/64 atoms][128][128 B]
+    // (over the dead attention operands); this CTA then computes out[:, head*D .. +D) = G Wo[head*D .. +D, :]^T over K = C with
+    // the weight k-blocks ([D rows][128 B]) streamed through NS2 stages placed behind G.
+    const int gbytes = 128 * p.C * 2;
+    uint8_t* sG = ring;
+    uint8_t* sW2 = ring + (gbytes > OPER_BYTES ? gbytes : OPER_BYTES);
+    const int NS2 = (p.C >> 6) < 4 ? (p.C >> 6) : 4;
+    float* s_ob = s_c1;                                // out_proj bias slice [D] (s_c1 is dead after the QKV read-out)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int head = blockIdx.y;
@@ -114,6 +127,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             mbar_init(&w_full[1], 1);
             mbar_init(o_ready, 8);
             mbar_init(out_full, 1);
+            for (int i = 0; i < 4; ++i) {
+                mbar_init(&w2_full[i], 1);
+                mbar_init(&w2_empty[i], 1);
+            }
+            mbar_init(out2_full, 1);
             fence_mbar_init();
         }
         __syncwarp();
@@ -126,6 +144,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     const uint32_t tmem = *tmem_slot;
     pdl_wait();
 
+    uint32_t okeep[2][16];   // gather mode: this thread's share of O_h (fp16 pairs), alive across the cluster barrier
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { okeep[0][i] = 0u; okeep[1][i] = 0u; }
     if (warp == 0) {
         if (lane == 0) {
             for (int kb = 0; kb < nkb; ++kb) {
@@ -135,7 +156,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                 tma_load_2d(ring + st * SB, &tmA, &full[st], kb * 64, m0);
                 tma_load_3d(ring + st * SB + CONV_A_BYTES, &tmB, &full[st], kb * 64, head * D, 0);
             }
-            if (p.fuse_out) {
+            if (p.fuse_out == 2) {
+                mbar_wait(accum_full, 0);                      // the ring is drained: the region behind G is free
+                for (int kb = 0; kb < NS2; ++kb) {
+                    mbar_arrive_expect_tx(&w2_full[kb], (uint32_t)(D * 128));
+                    tma_load_2d(sW2 + kb * (D * 128), &tmW, &w2_full[kb], kb * 64, head * D);
+                }
+            }
+            if (p.fuse_out == 1) {
                 mbar_wait(accum_full, 0);                      // the ring is drained: its tail is free for Wo
                 for (int hh = 0; hh < nhalf; ++hh) {
                     if (hh == 1 && !w1_early) mbar_wait(o_full, 0);
@@ -191,7 +219,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             }
             umma_commit(o_full);
             // ---- out_h = O_h Wo_h^T
-            if (p.fuse_out) {
+            if (p.fuse_out == 1) {
                 mbar_wait(o_ready, 0);
                 tc_fence_after();
                 const uint32_t idesc_w = umma_idesc_f16(128, NW);
@@ -366,7 +394,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             uint32_t v[32];
             tmem_ld32(tmem + lane_off + (uint32_t)(O_COL + c * 32), v);
             tmem_ld_wait();
-            if (p.fuse_out) {
+            if (p.fuse_out == 2) {
+                // keep this chunk (fp16) in registers: it is scattered to every head's CTA after the cluster barrier
+                const int kc = c >> 1;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const uint32_t pk = pack_h2(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+                    if (kc == 0) okeep[0][j] = pk; else okeep[1][j] = pk;
+                }
+            } else if (p.fuse_out) {
                 // O_h -> A operand (K-major, 128B swizzle) over the Q tile; padding columns keep Q's zeros
                 uint8_t* base = sQ + ((c * 32) >> 6) * CONV_A_BYTES + row * 128;
                 const int ch0 = ((c * 32) & 63) >> 3;
@@ -392,7 +428,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
                 }
             }
         }
-        if (p.fuse_out) {
+        if (p.fuse_out == 2) {
+            for (int i = threadIdx.x - 64; i < D; i += 256) s_ob[i] = __ldg(p.out_bias + head * D + i);
+            tc_fence_before();
+        }
+        if (p.fuse_out == 1) {
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -415,7 +455,124 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
             }
         }
     }
-    if (p.fuse_out) {
+    if (p.fuse_out == 2) {
+        const int heads = gridDim.y;
+        // (1) every CTA of the cluster is done with its attention operands -> their memory may be overwritten by the peers
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        if (warp >= 2) {
+            const int q = warp & 3, hf = (warp - 2) >> 2;
+            const int row = q * 32 + lane, sw = row & 7;
+            constexpr int OCH = D / 32;
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                const int c = hf + 2 * kc;
+                if (c < OCH) {
+                    const int col = head * D + c * 32;                       // first column of this chunk in the gathered [128][C]
+                    const uint32_t local = smem_u32(sG + (col >> 6) * CONV_A_BYTES + row * 128);
+                    const int ch0 = (col & 63) >> 3;
+                    for (int peer = 0; peer < heads; ++peer) {
+                        uint32_t remote;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(peer));
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t a = remote + (uint32_t)(((ch0 + j) ^ sw) << 4);
+                            asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(okeep[kc][4 * j]),
+                                         "r"(okeep[kc][4 * j + 1]), "r"(okeep[kc][4 * j + 2]), "r"(okeep[kc][4 * j + 3])
+                                         : "memory");
+                        }
+                    }
+                }
+            }
+        }
+        fence_proxy_async();            // writer side: generic-proxy (DSMEM) stores before the peers' tensor-core reads
+        // (2) all scatters have landed
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        fence_proxy_async();
+        tc_fence_after();
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int kb = NS2; kb < nkb; ++kb) {
+                    const int st = kb % NS2;
+                    mbar_wait(&w2_empty[st], ((kb / NS2) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&w2_full[st], (uint32_t)(D * 128));
+                    tma_load_2d(sW2 + st * (D * 128), &tmW, &w2_full[st], kb * 64, head * D);
+                }
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc_w = umma_idesc_f16(128, D);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    const int st = kb % NS2;
+                    mbar_wait(&w2_full[st], (kb / NS2) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_sw128(smem_u32(sG + kb * CONV_A_BYTES));
+                    const uint64_t dw = umma_desc_sw128(smem_u32(sW2 + st * (D * 128)));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16(tmem, da + (uint64_t)(k * 2), dw + (uint64_t)(k * 2), idesc_w, (kb | k) != 0);
+                    umma_commit(&w2_empty[st]);
+                }
+                umma_commit(out2_full);
+            }
+            __syncwarp();
+        } else {
+            const int q = warp & 3, hf = (warp - 2) >> 2;
+            const int row = q * 32 + lane;
+            const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+            const int grow = m0 + row;
+            const int growc = grow < p.M ? grow : p.M - 1;
+            constexpr int OCH = D / 32;
+            // residual rows are fetched before waiting for the MMA
+            uint4 res[2][4];
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                const int c = hf + 2 * kc;
+                if (c < OCH) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (size_t)growc * p.C + head * D + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) res[kc][j] = __ldg(rp + j);
+                }
+            }
+            mbar_wait(out2_full, 0);
+            tc_fence_after();
+#pragma unroll
+            for (int kc = 0; kc < 2; ++kc) {
+                const int c = hf + 2 * kc;
+                if (c < OCH) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem + lane_off + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    if (grow < p.M) {
+                        uint4* op = reinterpret_cast<uint4*>(p.out_final + (size_t)grow * p.C + head * D + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j * 8 + e]) + s_ob[c * 32 + j * 8 + e];
+                            const uint4 r4 = res[kc][j];
+                            float2 t;
+                            t = unpack_h2(r4.x); f[0] += t.x; f[1] += t.y;
+                            t = unpack_h2(r4.y); f[2] += t.x; f[3] += t.y;
+                            t = unpack_h2(r4.z); f[4] += t.x; f[5] += t.y;
+                            t = unpack_h2(r4.w); f[6] += t.x; f[7] += t.y;
+                            if (p.final_act == 1) {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                            }
+                            uint4 o;
+                            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
+                            o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+                            op[j] = o;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (p.fuse_out == 1) {
         // every head of the tile has written its partial; CTA `head` finalises 128/heads rows in fixed head order
         // barrier.cluster arrive.release / wait.acquire order the partial-tile writes (st.global.cg) before the peers' ld.global.cg
         cluster_arrive_release();
@@ -513,14 +670,25 @@ inline int attn_block_plan_build(AttnBlockPlan& pl, const f16* x, const f16* w, 
 // Adds the fused out-projection: wo = out_proj.weight [C][C] fp16 (K-major), ws = fp32 workspace of attn_block_ws_floats().
 inline size_t attn_block_ws_floats(int M, int C, int heads) { return (size_t)((M + 127) / 128) * heads * 128 * C; }
 inline bool attn_block_out_supported(int C, int heads) { return heads <= 8 && (128 % heads) == 0 && C <= 512 && (C <= 256 || C == 512); }
+// mode 1: per-head fp32 partials through the L2 workspace `ws`; mode 2: fp16 head outputs gathered through DSMEM (ws unused).
+inline bool attn_block_gather_supported(int C, int heads) {
+    if (heads > 8 || C % heads != 0) return false;
+    const int D = C / heads;
+    const int ring = (D == 128 ? 3 : 4) * (CONV_A_BYTES + 3 * D * 128);
+    const int dpad = D < 64 ? 64 : D;
+    const int oper = 2 * (dpad / 64) * CONV_A_BYTES + 2 * D * 128;
+    const int g = 128 * C * 2;
+    const int ns = (C / 64) < 4 ? (C / 64) : 4;
+    return (g > oper ? g : oper) + ns * D * 128 <= ring;
+}
 inline int attn_block_plan_fuse_out(AttnBlockPlan& pl, const f16* wo, const float* out_bias, const f16* residual, f16* out_final,
-                                    float* ws, int final_act) {
+                                    float* ws, int final_act, int mode = 1) {
     const int C = pl.p.C;
     uint64_t wd[2] = {(uint64_t)C, (uint64_t)C};
     uint64_t wsb[1] = {(uint64_t)C * 2};
-    uint32_t wb[2] = {64, (uint32_t)(C > 256 ? 256 : C)};
+    uint32_t wb[2] = {64, (uint32_t)(mode == 2 ? pl.D : (C > 256 ? 256 : C))};
     B2D_TRY(make_tmap_f16(&pl.tmW, wo, 2, wd, wsb, wb));
-    pl.p.fuse_out = 1;
+    pl.p.fuse_out = mode;
     pl.p.out_bias = out_bias; pl.p.residual = residual; pl.p.out_final = out_final; pl.p.ws = ws; pl.p.final_act = final_act;
     return 0;
 }

@@ -509,13 +509,17 @@ struct Builder {
                                       rows, C, L, heads) != 0) { err = -1; return; }
             static const bool no_out_fuse = getenv("B2D_NO_ATTN_OUT_FUSE") != nullptr;
             static const int out_fuse_maxc = getenv("B2D_ATTN_OUT_FUSE_MAXC") ? atoi(getenv("B2D_ATTN_OUT_FUSE_MAXC")) : 128;
-            fused_out = !no_out_fuse && attn_block_out_supported(C, heads) && C <= out_fuse_maxc;
+            // gather mode (fp16 head outputs exchanged through DSMEM, out-projection for every C inside the block): measured 1 %
+            // SLOWER per step than the separate conv_tc out-projection (the block only has heads x tiles CTAs) -> opt-in
+            static const bool want_gather = getenv("B2D_ATTN_GATHER") != nullptr;
+            const bool gather = !no_out_fuse && want_gather && attn_block_gather_supported(C, heads);
+            fused_out = gather || (!no_out_fuse && attn_block_out_supported(C, heads) && C <= out_fuse_maxc);
             double fl = 6.0 * rows * C * C + 4.0 * (double)L * L * C * B, by = 4.0 * rows * C + 6.0 * C * C;
             if (fused_out) {   // + out-projection, bias, residual (and the decoder's ReLU): the whole block is one launch
                 float* ws = nullptr;
-                if (h->alloc(&ws, attn_block_ws_floats(rows, C, heads)) != 0) { err = -2; return; }
+                if (!gather && h->alloc(&ws, attn_block_ws_floats(rows, C, heads)) != 0) { err = -2; return; }
                 if (attn_block_plan_fuse_out(*pl, W<f16>(role + ".out.w"), W<float>(role + ".out.b"), x,
-                                             h->cfg.attn_ff ? s_mid : out, ws, h->cfg.attn_ff ? 0 : final_act) != 0) { err = -1; return; }
+                                             h->cfg.attn_ff ? s_mid : out, ws, h->cfg.attn_ff ? 0 : final_act, gather ? 2 : 1) != 0) { err = -1; return; }
                 fl += 2.0 * rows * C * C;
                 by += 4.0 * rows * C + 2.0 * C * C;
             }
@@ -1475,7 +1479,8 @@ int b2d_op_attn_block_out(const void* x, const void* w_folded, const float* c1, 
     B2D_TRY(attn_block_plan_build(pl, (const f16*)x, (const f16*)w_folded, c1, bias, nullptr, B * L, C, L, heads));
     float* ws = nullptr;
     B2D_CUDA(cudaMalloc(&ws, attn_block_ws_floats(B * L, C, heads) * sizeof(float)));
-    int rc = attn_block_plan_fuse_out(pl, (const f16*)wo, out_bias, (const f16*)x, (f16*)y, ws, final_act);
+    const bool gather = getenv("B2D_NO_ATTN_GATHER") == nullptr && attn_block_gather_supported(C, heads);
+    int rc = attn_block_plan_fuse_out(pl, (const f16*)wo, out_bias, (const f16*)x, (f16*)y, ws, final_act, gather ? 2 : 1);
     if (rc == 0) rc = attn_block_launch(pl, as_stream(stream));
     cudaStreamSynchronize(as_stream(stream));
     cudaFree(ws);
