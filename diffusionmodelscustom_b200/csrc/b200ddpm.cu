@@ -817,7 +817,6 @@ static int init_uniform_carveout() {
     B2D_TRY(set_carveout(instnorm_apply_kernel));
     B2D_TRY(set_carveout(tail_conv_kernel));
     B2D_TRY(set_carveout(posterior_update_kernel));
-    B2D_TRY(set_carveout(step_advance_kernel));
     B2D_TRY(set_carveout(fill_int_kernel));
     B2D_TRY(set_carveout(bicubic_resize_kernel));
     B2D_TRY(set_carveout(sample_stats_kernel));

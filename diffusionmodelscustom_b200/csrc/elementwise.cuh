@@ -754,16 +754,6 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
         }
     }
 }
-// Stand-alone form of the step advance (kept for plain-stream debugging): i <- i-1 and t[b] <- i-1.
-__global__ void step_advance_kernel(int* step_ptr, int* t_arr, int B) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int i = *step_ptr - 1;
-    __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x) t_arr[b] = i;
-    if (threadIdx.x == 0) *step_ptr = i;
-}
-
 __global__ void fill_int_kernel(int* p, int v, int n) {
     pdl_launch_dependents();
     pdl_wait();
