@@ -469,13 +469,18 @@ struct Builder {
         } else {
             if (conv_plan_build(*pl, h->num_sms) != 0) { err = -1; return; }
             static const bool no_gn_epi = getenv("B2D_NO_GN_EPILOGUE") != nullptr;
-            if (want_gn && !no_gn_epi && pl->p.splits == 1 && pl->p.TN == 1 && !convt) {
-                const int mtiles = (int)pl->grid.x, ntiles = (int)pl->grid.y;
+            const int hw_out = pl->p.Ho * pl->p.Wo;
+            const bool gn_whole = pl->p.TN == 1;                                   // a tile lies inside one sample
+            const bool gn_quarter = pl->p.TN > 1 && hw_out % 32 == 0;              // several samples per tile, 32-row quarters do not straddle
+            if (want_gn && !no_gn_epi && pl->p.splits == 1 && (gn_whole || gn_quarter) && !convt) {
+                const int sub = gn_whole ? 1 : 4;
+                const int mtiles = (int)pl->grid.x * sub, ntiles = (int)pl->grid.y;
                 float* part = nullptr;
                 if (h->alloc(&part, (size_t)mtiles * ntiles * 2) != 0) { err = -2; return; }
                 pl->p.gn_partial = part;
+                pl->p.gn_sub = sub;
                 last_gn_partial = part;
-                last_gn_tps = pl->p.tiles_w * pl->p.tiles_h;
+                last_gn_tps = gn_whole ? pl->p.tiles_w * pl->p.tiles_h : hw_out / 32;
                 last_gn_ntiles = ntiles;
                 last_gn_mtiles = mtiles;
             }

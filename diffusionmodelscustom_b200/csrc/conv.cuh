@@ -42,6 +42,7 @@ struct ConvParams {
     // GroupNorm(1,C) statistics of the OUTPUT fused into the epilogue (conv_tc, unsplit, one sample per M tile): every CTA
     // writes {sum, sum of squares} of its tile to gn_partial[(nblk * mtiles + mtile) * 2]; the consumer adds them in order.
     float* gn_partial;
+    int gn_sub;          // 1: one {sum, sumsq} per 128-row tile; 4: one per 32-row quarter (tiles that span several samples)
     // split-K: gridDim.z = splits CTAs of one cluster share an output tile; fp32 partials go through `ws`
     int splits;
     float* ws;  // [tiles][splits][128][BN] fp32
@@ -397,7 +398,13 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                     s_bias[2 * (warp - 2) + 1] = gs2;
                 }
                 named_bar_sync(1, 128);
-                if (threadIdx.x == 64) {
+                if (p.gn_sub == 4) {                               // per 32-row quarter (row order: quarter q = warp & 3)
+                    if (lane == 0) {
+                        const size_t t = (((size_t)nblk * gridDim.x + blockIdx.x) * 4 + q) * 2;
+                        p.gn_partial[t] = gs1;
+                        p.gn_partial[t + 1] = gs2;
+                    }
+                } else if (threadIdx.x == 64) {
                     const size_t t = ((size_t)nblk * gridDim.x + blockIdx.x) * 2;
                     p.gn_partial[t] = (s_bias[0] + s_bias[2]) + (s_bias[4] + s_bias[6]);
                     p.gn_partial[t + 1] = (s_bias[1] + s_bias[3]) + (s_bias[5] + s_bias[7]);
