@@ -16,7 +16,7 @@ FAMILY_R, FAMILY_D = 0, 1
 # every symbol include/b200ddpm.h declares (tests check that the library exports all of them)
 SYMBOLS = ["b2d_last_error", "b2d_abi_version", "b2d_create", "b2d_destroy", "b2d_load_weights", "b2d_set_schedule",
            "b2d_set_conditioning", "b2d_forward", "b2d_sample", "b2d_sample_host", "b2d_last_launch_count", "b2d_debug_read", "b2d_profile_step",
-           "b2d_op_conv2d", "b2d_op_layernorm", "b2d_op_attention", "b2d_op_attn_block", "b2d_op_attn_block_out", "b2d_op_instnorm", "b2d_op_posterior_update"]
+           "b2d_op_conv2d", "b2d_op_layernorm", "b2d_op_attention", "b2d_op_attn_block", "b2d_op_attn_block_out", "b2d_op_instnorm", "b2d_op_posterior_update", "b2d_saturation_count"]
 
 
 class Config(C.Structure):
@@ -75,6 +75,8 @@ def lib():
                                      [C.c_int32] * 3 + [C.c_void_p]
         L.b2d_op_posterior_update.argtypes = [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_int64, C.c_uint64, C.c_uint64,
                                                                  C.c_float, C.c_void_p]
+        L.b2d_saturation_count.argtypes = [C.c_int32]
+        L.b2d_saturation_count.restype = C.c_uint32
         if L.b2d_abi_version() != 1:
             raise NativeError("libb200ddpm.so ABI version mismatch")
         _lib = L

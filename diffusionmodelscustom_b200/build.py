@@ -14,8 +14,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libb200ddpm.so")
 SOURCES = ["b200ddpm.cu"]
-HEADERS = ["common.cuh", "conv.cuh", "attention.cuh", "attention_tc.cuh", "gemm_stream.cuh", "norm_fused.cuh", "elementwise.cuh", "family_d.cuh",
-           os.path.join("..", "..", "include", "b200ddpm.h")]
+# every header the translation unit includes: a stale-check over the whole csrc/ directory, so that a new .cuh can never be forgotten
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + [os.path.join("..", "..", "include", "b200ddpm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -91,32 +91,24 @@ struct Handle {
     float* d_cond_pre = nullptr;    // [B][H/2][H/2][64] fp32 : conv1 contribution of the conditioning channels
     float* d_temb = nullptr;        // [B][n_temb]
     int n_temb = 0;
-    float* d_x_stage = nullptr;  // device staging for the host entry point
     float* d_noise_stage = nullptr;
     size_t noise_stage_elems = 0;
 
-    // sampling graph cache
-    cudaGraphExec_t graph_exec = nullptr;
-    struct GraphKey {
-        int B = 0;
-        const void *x = nullptr, *noise = nullptr;
-        uint64_t seed = 0, off = 0;
-        float scale = 0;
-        bool operator==(const GraphKey& o) const {
-            return B == o.B && x == o.x && noise == o.noise && seed == o.seed && off == o.off && scale == o.scale;
-        }
-    } graph_key;
-    int graph_nodes = 0;
+    // Sampling graphs.  Everything a sampling job can change between calls (the state pointer, host-injected noise, seed, sample
+    // offset, noise scale) lives in the device-resident SampleJob block that posterior_update_kernel reads, and the state itself
+    // is the handle's own d_x_work buffer, so the graphs depend on (program, schedule tables, has_y) only and are captured ONCE:
+    // graph_multi holds `graph_steps` consecutive reverse steps (PDL overlap spans the step boundaries), graph_one a single
+    // step for the remainder of (T-1) / graph_steps.
+    cudaGraphExec_t graph_multi = nullptr, graph_one = nullptr;
+    int graph_steps = 0, graph_nodes_multi = 0, graph_nodes_one = 0;
+    SampleJob* d_job = nullptr;
+    float* d_x_work = nullptr;       // [max_batch][c_hr][H][H] fp32: the diffusion state of the running job
+    // host-entry staging (allocated once with the handle: no cudaMalloc/cudaFree inside b2d_sample_host)
+    float *d_lsm_stage = nullptr, *d_topo_stage = nullptr, *d_cond_stage = nullptr;
+    size_t cond_stage_elems = 0;
+    int* h_y_pinned = nullptr;       // pinned int32 labels for the host entry
     int64_t last_launches = 0;
     cudaStream_t own_stream = nullptr;
-    // Micro-batch splitting: at small per-GPU batches most launches are latency-bound and fill a fraction of the SMs, so
-    // the batch is cut into `kids.size()` contiguous sub-batches whose step programs run as CONCURRENT branches of the
-    // captured graph (fork/join with events).  Kids share the parent's packed weights and own their activations.
-    std::vector<Handle*> kids;
-    std::vector<int> kid_b0, kid_B;
-    bool is_kid = false;
-    cudaEvent_t ev_fork = nullptr;
-    std::vector<cudaEvent_t> ev_join;
     // Time-embedding pipelining inside the reverse loop: d_temb depends on the step index only, so the projections for
     // step i-1 are launched on a side stream as soon as step i's last reader of d_temb has been enqueued, and overlap the
     // final layer + posterior update (a concurrent branch of the captured step graph).
@@ -143,17 +135,21 @@ struct Handle {
         taps.clear();
         prog_B = 0;
     }
-    void free_kids() {
-        for (Handle* k : kids) delete k;
-        kids.clear();
-        kid_b0.clear();
-        kid_B.clear();
+    void drop_graphs() {
+        if (graph_multi) cudaGraphExecDestroy(graph_multi);
+        if (graph_one) cudaGraphExecDestroy(graph_one);
+        graph_multi = graph_one = nullptr;
+    }
+    // cudaFree of one long-lived allocation (schedule tables / noise staging that are re-sized)
+    void release(void* p) {
+        if (!p) return;
+        for (auto it = allocs.begin(); it != allocs.end(); ++it)
+            if (*it == p) { allocs.erase(it); break; }
+        cudaFree(p);
     }
     ~Handle() {
-        if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        free_kids();
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        for (auto e : ev_join) cudaEventDestroy(e);
+        drop_graphs();
+        if (h_y_pinned) cudaFreeHost(h_y_pinned);
         free_program();
         for (void* p : allocs) cudaFree(p);
         if (own_stream) cudaStreamDestroy(own_stream);
@@ -857,72 +853,11 @@ static int init_batch_buffers(Handle* h) {
     return 0;
 }
 
-// Number of concurrent sub-batches for a batch of B (B2D_SPLIT in the environment overrides; sub-batches >= 8 samples).
-static int split_count(const Handle* h, int B) {
-    if (h->is_kid) return 1;
-    static const int env = getenv("B2D_SPLIT") ? atoi(getenv("B2D_SPLIT")) : 0;
-    int n = env > 0 ? env : 1;   // measured on B200: no gain at batch 64 (per-CTA latency, not grid size, paces the launches)
-    while (n > 1 && B / n < 8) n >>= 1;
-    return n < 1 ? 1 : n;
-}
-
-static int ensure_program(Handle* h, int B);
-
-static int ensure_kids(Handle* h, int B, int n) {
-    bool ok = (int)h->kids.size() == n;
-    for (int i = 0; ok && i < n; ++i) {
-        const int lo = (int)((long long)B * i / n), hi = (int)((long long)B * (i + 1) / n);
-        ok = h->kid_b0[i] == lo && h->kid_B[i] == hi - lo;
-    }
-    if (ok) return 0;
-    if (h->graph_exec) {
-        cudaGraphExecDestroy(h->graph_exec);
-        h->graph_exec = nullptr;
-    }
-    h->free_kids();
-    if (!h->ev_fork) B2D_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    while ((int)h->ev_join.size() < n) {
-        cudaEvent_t e;
-        B2D_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        h->ev_join.push_back(e);
-    }
-    for (int i = 0; i < n; ++i) {
-        const int lo = (int)((long long)B * i / n), hi = (int)((long long)B * (i + 1) / n);
-        Handle* k = new b2d_handle();
-        h->kids.push_back(k);
-        h->kid_b0.push_back(lo);
-        h->kid_B.push_back(hi - lo);
-        k->cfg = h->cfg;
-        k->cfg.max_batch = hi - lo;
-        k->num_sms = h->num_sms;
-        k->is_kid = true;
-        k->dev = h->dev;             // shared packed weights (owned by the parent)
-        k->weights_loaded = true;
-        B2D_TRY(init_batch_buffers(k));
-        B2D_TRY(ensure_program(k, hi - lo));
-    }
-    return 0;
-}
-
 static int ensure_program(Handle* h, int B) {
     B2D_CHECK(h->weights_loaded, "b2d_load_weights has not been called");
     B2D_CHECK(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch of the handle");
-    const int nsplit = split_count(h, B);
-    if (nsplit > 1) {
-        h->free_program();
-        B2D_TRY(ensure_kids(h, B, nsplit));
-        h->prog_B = B;
-        return 0;
-    }
-    if (!h->kids.empty()) {
-        h->free_kids();
-        h->prog_B = 0;
-    }
     if (h->prog_B == B) return 0;
-    if (h->graph_exec) {
-        cudaGraphExecDestroy(h->graph_exec);
-        h->graph_exec = nullptr;
-    }
+    h->drop_graphs();
     h->free_program();
     h->in_prog = true;
     const int rc = (h->cfg.family == B2D_FAMILY_R) ? build_program_r(h, B) : build_program_d(h, B);
@@ -1030,9 +965,21 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = norm_fused_init_attrs())) break;
         if ((rc = init_uniform_carveout())) break;
         const int B = cfg->max_batch, H = cfg->img_size;
-        const size_t n = (size_t)B * cfg->c_hr * H * H;
+        const size_t n = (size_t)B * cfg->c_hr * H * H, plane = (size_t)H * H;
         if ((rc = init_batch_buffers(h))) break;
-        if ((rc = h->alloc(&h->d_x_stage, n))) break;
+        if ((rc = h->alloc(&h->d_x_work, n))) break;
+        if ((rc = h->alloc(&h->d_job, 1))) break;
+        // staging of the host entry point (b2d_sample_host): sized once, never re-allocated per call
+        if (cfg->family == B2D_FAMILY_R) {
+            if (cfg->has_lsm && (rc = h->alloc(&h->d_lsm_stage, (size_t)B * plane))) break;
+            if (cfg->has_topo && (rc = h->alloc(&h->d_topo_stage, (size_t)B * plane))) break;
+        }
+        h->cond_stage_elems = (size_t)B * std::max(cfg->cond_channels, 1) * plane;   // Family D low-res fields are smaller
+        if ((rc = h->alloc(&h->d_cond_stage, h->cond_stage_elems))) break;
+        if (cudaMallocHost(reinterpret_cast<void**>(&h->h_y_pinned), (size_t)B * sizeof(int)) != cudaSuccess) {
+            rc = fail(-2, "pinned label staging allocation failed");
+            break;
+        }
     } while (0);
     if (rc) {
         delete h;
@@ -1069,7 +1016,16 @@ int b2d_load_weights(b2d_handle* h, const b2d_tensor* tensors, int32_t n) {
 
 int b2d_set_schedule(b2d_handle* h, const float* betas, const float* alphas, const float* alpha_hat, int32_t T) {
     B2D_CHECK(h && betas && alphas && alpha_hat && T >= 2, "bad schedule");
+    // the tables may still be read by work queued earlier on any stream of this device
+    B2D_CUDA(cudaDeviceSynchronize());
     if (T != h->T) {
+        // the captured step graphs hold the table pointers: drop them together with the old tables
+        h->drop_graphs();
+        h->release(h->d_betas);
+        h->release(h->d_alphas);
+        h->release(h->d_alpha_hat);
+        h->d_betas = h->d_alphas = h->d_alpha_hat = nullptr;
+        h->T = 0;
         B2D_TRY(h->alloc(&h->d_betas, T));
         B2D_TRY(h->alloc(&h->d_alphas, T));
         B2D_TRY(h->alloc(&h->d_alpha_hat, T));
@@ -1081,41 +1037,34 @@ int b2d_set_schedule(b2d_handle* h, const float* betas, const float* alphas, con
     return 0;
 }
 
-int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, const float* cond, int32_t cond_h,
-                         int32_t cond_w, const int64_t* y, int32_t B, void* stream) {
+// y_dev: int64 labels in device memory (synchronises once to range-check them, as nn.Embedding would raise);
+// y_host: the same in host memory (no device round trip).  At most one of them is non-null.
+static int set_conditioning_impl(b2d_handle* h, const float* lsm, const float* topo, const float* cond, int32_t cond_h,
+                                 int32_t cond_w, const int64_t* y_dev, const int64_t* y_host, int32_t B, cudaStream_t st) {
     B2D_CHECK(h, "null handle");
     B2D_TRY(ensure_program(h, B));
-    cudaStream_t st = as_stream(stream);
     const b2d_config& c = h->cfg;
     const int H = c.img_size;
-    if (!h->kids.empty()) {
-        const size_t plane = (size_t)H * H;
-        const size_t cond_per = (c.family == B2D_FAMILY_D) ? (size_t)c.cond_channels * cond_h * cond_w
-                                                           : (size_t)c.cond_channels * plane;
-        for (size_t i = 0; i < h->kids.size(); ++i) {
-            const int b0 = h->kid_b0[i];
-            B2D_TRY(b2d_set_conditioning(static_cast<b2d_handle*>(h->kids[i]), lsm ? lsm + b0 * plane : nullptr,
-                                         topo ? topo + b0 * plane : nullptr, cond ? cond + b0 * cond_per : nullptr, cond_h,
-                                         cond_w, y ? y + b0 : nullptr, h->kid_B[i], stream));
-        }
-        h->has_y = (y != nullptr);
-        return 0;
-    }
-    if (y) {
+    const bool has_y = (y_dev != nullptr || y_host != nullptr);
+    if (has_y) {
         B2D_CHECK(c.num_classes > 0, "y given but the model has no label embedding");
-        // int64 -> int32 on device
-        std::vector<int64_t> tmp(B);
-        B2D_CUDA(cudaMemcpyAsync(tmp.data(), y, B * 8, cudaMemcpyDeviceToHost, st));
-        B2D_CUDA(cudaStreamSynchronize(st));
-        std::vector<int> yi(B);
-        for (int i = 0; i < B; ++i) {
-            B2D_CHECK(tmp[i] >= 0 && tmp[i] < c.num_classes, "class label out of range");
-            yi[i] = (int)tmp[i];
+        std::vector<int64_t> tmp;
+        if (y_dev) {
+            tmp.resize(B);
+            B2D_CUDA(cudaMemcpyAsync(tmp.data(), y_dev, B * 8, cudaMemcpyDeviceToHost, st));
+            B2D_CUDA(cudaStreamSynchronize(st));
+            y_host = tmp.data();
+        } else {
+            B2D_CUDA(cudaStreamSynchronize(st));   // h_y_pinned may still be the source of an earlier upload
         }
-        B2D_CUDA(cudaMemcpyAsync(h->d_y, yi.data(), B * 4, cudaMemcpyHostToDevice, st));
-        B2D_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < B; ++i) {
+            B2D_CHECK(y_host[i] >= 0 && y_host[i] < c.num_classes, "class label out of range");
+            h->h_y_pinned[i] = (int)y_host[i];
+        }
+        B2D_CUDA(cudaMemcpyAsync(h->d_y, h->h_y_pinned, B * 4, cudaMemcpyHostToDevice, st));
     }
-    h->has_y = (y != nullptr);
+    if (has_y != h->has_y) h->drop_graphs();   // the time-embedding launch of a captured graph holds (has_y ? d_y : null)
+    h->has_y = has_y;
     if (c.family == B2D_FAMILY_D) return set_conditioning_d(h, cond, cond_h, cond_w, B, st);
     // Family R: stack [lsm, topo, cond] (concat order of Encoder.forward :228-238) per sample, then conv1's share of it
     B2D_CHECK(!c.has_lsm || lsm, "model was built with lsm_tensor: lsm_cond is required");
@@ -1143,28 +1092,15 @@ int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, con
     return 0;
 }
 
+int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, const float* cond, int32_t cond_h,
+                         int32_t cond_w, const int64_t* y, int32_t B, void* stream) {
+    return set_conditioning_impl(h, lsm, topo, cond, cond_h, cond_w, y, nullptr, B, as_stream(stream));
+}
+
 int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps_out, int32_t B, void* stream) {
     B2D_CHECK(h && x && t_host && eps_out, "null argument");
     B2D_TRY(ensure_program(h, B));
     cudaStream_t st = as_stream(stream);
-    if (!h->kids.empty()) {
-        const size_t per_in = (size_t)h->cfg.c_hr * h->cfg.img_size * h->cfg.img_size;
-        const size_t per_out = (size_t)h->cfg.c_out * h->cfg.img_size * h->cfg.img_size;
-        B2D_CUDA(cudaEventRecord(h->ev_fork, st));
-        int64_t launches = 0;
-        for (size_t i = 0; i < h->kids.size(); ++i) {
-            Handle* k = h->kids[i];
-            const int b0 = h->kid_b0[i];
-            B2D_CUDA(cudaStreamWaitEvent(k->own_stream, h->ev_fork, 0));
-            B2D_TRY(b2d_forward(static_cast<b2d_handle*>(k), x + b0 * per_in, t_host + b0, eps_out + b0 * per_out, h->kid_B[i],
-                                k->own_stream));
-            B2D_CUDA(cudaEventRecord(h->ev_join[i], k->own_stream));
-            B2D_CUDA(cudaStreamWaitEvent(st, h->ev_join[i], 0));
-            launches += k->last_launches;
-        }
-        h->last_launches = launches;
-        return 0;
-    }
     std::vector<int> ti(B);
     for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
     B2D_CUDA(cudaMemcpyAsync(h->d_t, ti.data(), B * 4, cudaMemcpyHostToDevice, st));
@@ -1176,162 +1112,140 @@ int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps
     return 0;
 }
 
-int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed, uint64_t sample_offset,
-               float noise_scale, int32_t B, void* stream) {
-    B2D_CHECK(h && x_inout, "null argument");
-    B2D_CHECK(h->T >= 2, "b2d_set_schedule has not been called");
-    B2D_TRY(ensure_program(h, B));
-    cudaStream_t st = as_stream(stream);
+// One reverse step on stream `st`: the eps program on d_x_work, then the posterior update (whose last block advances i and t).
+static int enqueue_reverse_step(b2d_handle* h, int B, cudaStream_t st) {
     const b2d_config& c = h->cfg;
     const size_t per_sample = (size_t)c.c_hr * c.img_size * c.img_size;
     const size_t n = per_sample * B;
+    h->cur_x = h->d_x_work;
+    h->cur_eps = h->d_eps;
+    B2D_TRY(run_step_ops(h, st, true));
+    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)h->num_sms * 8);
+    B2D_TRY(join_temb_side(h, st));   // the update's last block advances d_t, which the side branch reads
+    B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, h->d_x_work, h->d_eps, h->d_job, h->d_alphas,
+                      h->d_betas, h->d_alpha_hat, h->d_step, h->d_t, B, n, per_sample));
+    return 0;
+}
+
+static int capture_steps(b2d_handle* h, int B, int nsteps, cudaGraphExec_t* out, int* nodes_out) {
+    cudaStream_t cs = h->own_stream;
+    B2D_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int s = 0; s < nsteps && rc == 0; ++s) rc = enqueue_reverse_step(h, B, cs);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    B2D_CUDA(ce);
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    *nodes_out = (int)nn;
+    cudaError_t ie = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    B2D_CUDA(ie);
+    return 0;
+}
+
+// The loop on the handle's own state buffer d_x_work (already filled by the caller, on `st`).
+static int sample_core(b2d_handle* h, const float* noise, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B,
+                       cudaStream_t st) {
+    B2D_CHECK(h->T >= 2, "b2d_set_schedule has not been called");
+    const b2d_config& c = h->cfg;
     B2D_CHECK(c.c_hr == c.c_out, "sampling needs c_out == c_hr");
-    Handle::GraphKey key;
-    key.B = B; key.x = x_inout; key.noise = noise; key.seed = seed; key.off = sample_offset; key.scale = noise_scale;
-    // parts: the handle itself, or its concurrent sub-batch kids
-    struct Part { Handle* ph; int b0, Bi; };
-    std::vector<Part> parts;
-    if (h->kids.empty()) parts.push_back({h, 0, B});
-    else for (size_t i = 0; i < h->kids.size(); ++i) parts.push_back({h->kids[i], h->kid_b0[i], h->kid_B[i]});
-    static const bool no_graph = getenv("B2D_NO_GRAPH") != nullptr;   // A/B: plain stream launches (PDL) instead of a graph
+    const size_t per_sample = (size_t)c.c_hr * c.img_size * c.img_size;
+    const int T = h->T;
+    SampleJob job{};
+    job.noise = noise;
+    job.seed = seed;
+    job.sample_offset = sample_offset;
+    job.noise_stride = per_sample * B;
+    job.noise_scale = noise_scale;
+    B2D_CUDA(launch_k(set_job_kernel, dim3(1), dim3(256), 0, st, h->d_job, job, h->d_t, h->d_step, T - 1, B));
+    static const bool no_graph = getenv("B2D_NO_GRAPH") != nullptr;   // A/B: plain stream launches (PDL) instead of graphs
+    if (temb_pipelined(h)) B2D_TRY(h->step_ops[0](st));   // embeddings of the first step; later ones come from the side branch
     if (no_graph) {
-        const int T = h->T;
-        for (auto& p : parts) {
-            B2D_CUDA(launch_k(fill_int_kernel, dim3((p.Bi + 255) / 256), dim3(256), 0, st, p.ph->d_t, T - 1, p.Bi));
-            B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, p.ph->d_step, T - 1, 1));
-            if (temb_pipelined(p.ph)) B2D_TRY(p.ph->step_ops[0](st));   // embeddings of the first step; later ones come from the side branch
-        }
-        int64_t launches = 0;
-        for (int i = T - 1; i >= 1; --i) {
-            for (auto& p : parts) {
-                float* xs = x_inout + (size_t)p.b0 * per_sample;
-                p.ph->cur_x = xs;
-                p.ph->cur_eps = p.ph->d_eps;
-                B2D_TRY(run_step_ops(p.ph, st, true));
-                const size_t ni = per_sample * p.Bi;
-                const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
-                B2D_TRY(join_temb_side(p.ph, st));   // the update's last block advances d_t, which the side branch reads
-                B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, xs, p.ph->d_eps,
-                                  noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
-                                  p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
-                                  noise_scale, n));
-                launches += (int64_t)p.ph->step_ops.size() + 1;
-            }
-        }
-        h->last_launches = launches;
+        for (int i = T - 1; i >= 1; --i) B2D_TRY(enqueue_reverse_step(h, B, st));
+        h->last_launches = ((int64_t)h->step_ops.size() + 1) * (T - 1) + 2;
         return 0;
     }
-    if (!h->graph_exec || !(key == h->graph_key)) {
-        if (h->graph_exec) {
-            cudaGraphExecDestroy(h->graph_exec);
-            h->graph_exec = nullptr;
-        }
-        // capture ONE reverse step; the step index lives in device memory so the same graph serves every i.
-        // Sub-batches are forked onto their own streams inside the capture => concurrent branches of the graph.
-        cudaStream_t cs = h->own_stream;
-        B2D_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        auto body = [&]() -> int {
-            if (parts.size() > 1) B2D_CUDA(cudaEventRecord(h->ev_fork, cs));
-            for (size_t i = 0; i < parts.size(); ++i) {
-                Part& p = parts[i];
-                cudaStream_t si = (i == 0) ? cs : p.ph->own_stream;
-                if (i > 0) B2D_CUDA(cudaStreamWaitEvent(si, h->ev_fork, 0));
-                float* xs = x_inout + (size_t)p.b0 * per_sample;
-                p.ph->cur_x = xs;
-                p.ph->cur_eps = p.ph->d_eps;
-                B2D_TRY(run_step_ops(p.ph, si, true));
-                const size_t ni = per_sample * p.Bi;
-                const int blocks = (int)std::min<size_t>((ni / 4 + 255) / 256, (size_t)h->num_sms * 8);
-                B2D_TRY(join_temb_side(p.ph, si));   // the update's last block advances d_t, which the side branch reads
-                B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, si, xs, p.ph->d_eps,
-                                  noise ? noise + (size_t)p.b0 * per_sample : nullptr, h->d_alphas, h->d_betas, h->d_alpha_hat,
-                                  p.ph->d_step, p.ph->d_t, p.Bi, ni, per_sample, seed, sample_offset + (uint64_t)p.b0,
-                                  noise_scale, n));
-                if (i > 0) {
-                    B2D_CUDA(cudaEventRecord(h->ev_join[i], si));
-                    B2D_CUDA(cudaStreamWaitEvent(cs, h->ev_join[i], 0));
-                }
-            }
-            return 0;
-        };
-        int rc = body();
-        cudaGraph_t graph = nullptr;
-        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-        if (rc) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
-        }
-        B2D_CUDA(ce);
-        size_t nn = 0;
-        cudaGraphGetNodes(graph, nullptr, &nn);
-        h->graph_nodes = (int)nn;
-        cudaError_t ie = cudaGraphInstantiate(&h->graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        B2D_CUDA(ie);
-        h->graph_key = key;
+    static const int env_steps = getenv("B2D_GRAPH_STEPS") ? atoi(getenv("B2D_GRAPH_STEPS")) : 8;
+    const int gs = std::max(1, std::min(env_steps, T - 1));
+    if (h->graph_steps != gs) {
+        h->drop_graphs();
+        h->graph_steps = gs;
     }
-    const int T = h->T;
-    for (auto& p : parts) {
-        B2D_CUDA(launch_k(fill_int_kernel, dim3((p.Bi + 255) / 256), dim3(256), 0, st, p.ph->d_t, T - 1, p.Bi));
-        B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, p.ph->d_step, T - 1, 1));
-        if (temb_pipelined(p.ph)) B2D_TRY(p.ph->step_ops[0](st));   // embeddings of the first step; later ones come from the side branch
+    if (!h->graph_one) B2D_TRY(capture_steps(h, B, 1, &h->graph_one, &h->graph_nodes_one));
+    if (gs > 1 && !h->graph_multi) B2D_TRY(capture_steps(h, B, gs, &h->graph_multi, &h->graph_nodes_multi));
+    const int n_multi = gs > 1 ? (T - 1) / gs : 0, n_one = (T - 1) - n_multi * gs;
+    for (int k = 0; k < n_multi; ++k) B2D_CUDA(cudaGraphLaunch(h->graph_multi, st));
+    for (int k = 0; k < n_one; ++k) B2D_CUDA(cudaGraphLaunch(h->graph_one, st));
+    h->last_launches = (int64_t)h->graph_nodes_multi * n_multi + (int64_t)h->graph_nodes_one * n_one + 2;
+    return 0;
+}
+
+int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed, uint64_t sample_offset,
+               float noise_scale, int32_t B, void* stream) {
+    B2D_CHECK(h && x_inout, "null argument");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = as_stream(stream);
+    const size_t n = (size_t)h->cfg.c_hr * h->cfg.img_size * h->cfg.img_size * B;
+    B2D_CUDA(cudaMemcpyAsync(h->d_x_work, x_inout, n * 4, cudaMemcpyDeviceToDevice, st));
+    B2D_TRY(sample_core(h, noise, seed, sample_offset, noise_scale, B, st));
+    B2D_CUDA(cudaMemcpyAsync(x_inout, h->d_x_work, n * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// Host entry: enqueue only (uploads, loop, download into x_inout_host); b2d_sample_host adds the final synchronise, the
+// ensemble driver overlaps the next job's host work with it.
+static int sample_host_enqueue(b2d_handle* h, float* x_inout_host, const float* lsm_host, const float* topo_host,
+                               const float* cond_host, int32_t cond_h, int32_t cond_w, const int64_t* y_host,
+                               const float* noise_host, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B,
+                               cudaStream_t st) {
+    B2D_CHECK(h && x_inout_host, "null argument");
+    B2D_CHECK(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch of the handle");
+    const b2d_config& c = h->cfg;
+    const int H = c.img_size;
+    const size_t plane = (size_t)H * H;
+    const size_t n = (size_t)B * c.c_hr * plane;
+    B2D_CHECK(!lsm_host || h->d_lsm_stage, "lsm given but the model was built without lsm conditioning");
+    B2D_CHECK(!topo_host || h->d_topo_stage, "topo given but the model was built without topography conditioning");
+    const size_t cond_elems = !cond_host ? 0
+                              : (c.family == B2D_FAMILY_D) ? (size_t)B * c.cond_channels * cond_h * cond_w
+                                                           : (size_t)B * c.cond_channels * plane;
+    B2D_CHECK(cond_elems <= h->cond_stage_elems, "conditioning field larger than the handle's staging buffer");
+    B2D_CUDA(cudaMemcpyAsync(h->d_x_work, x_inout_host, n * 4, cudaMemcpyHostToDevice, st));
+    if (lsm_host) B2D_CUDA(cudaMemcpyAsync(h->d_lsm_stage, lsm_host, (size_t)B * plane * 4, cudaMemcpyHostToDevice, st));
+    if (topo_host) B2D_CUDA(cudaMemcpyAsync(h->d_topo_stage, topo_host, (size_t)B * plane * 4, cudaMemcpyHostToDevice, st));
+    if (cond_host) B2D_CUDA(cudaMemcpyAsync(h->d_cond_stage, cond_host, cond_elems * 4, cudaMemcpyHostToDevice, st));
+    if (noise_host) {
+        const size_t ne = (size_t)h->T * n;
+        if (ne > h->noise_stage_elems) {
+            B2D_CUDA(cudaStreamSynchronize(st));
+            h->release(h->d_noise_stage);
+            h->d_noise_stage = nullptr;
+            h->noise_stage_elems = 0;
+            B2D_TRY(h->alloc(&h->d_noise_stage, ne));
+            h->noise_stage_elems = ne;
+        }
+        B2D_CUDA(cudaMemcpyAsync(h->d_noise_stage, noise_host, ne * 4, cudaMemcpyHostToDevice, st));
     }
-    for (int i = T - 1; i >= 1; --i) B2D_CUDA(cudaGraphLaunch(h->graph_exec, st));
-    h->last_launches = (int64_t)h->graph_nodes * (T - 1) + 2 * (int64_t)parts.size();
+    B2D_TRY(set_conditioning_impl(h, lsm_host ? h->d_lsm_stage : nullptr, topo_host ? h->d_topo_stage : nullptr,
+                                  cond_host ? h->d_cond_stage : nullptr, cond_h, cond_w, nullptr, y_host, B, st));
+    B2D_TRY(sample_core(h, noise_host ? h->d_noise_stage : nullptr, seed, sample_offset, noise_scale, B, st));
+    B2D_CUDA(cudaMemcpyAsync(x_inout_host, h->d_x_work, n * 4, cudaMemcpyDeviceToHost, st));
     return 0;
 }
 
 int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, const float* topo_host,
                     const float* cond_host, int32_t cond_h, int32_t cond_w, const int64_t* y_host,
                     const float* noise_host, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B) {
-    B2D_CHECK(h && x_inout_host, "null argument");
-    B2D_CHECK(B >= 1 && B <= h->cfg.max_batch, "batch exceeds max_batch of the handle");
-    const b2d_config& c = h->cfg;
-    const int H = c.img_size;
+    B2D_CHECK(h, "null handle");
     cudaStream_t st = h->own_stream;
-    const size_t plane = (size_t)H * H;
-    const size_t n = (size_t)B * c.c_hr * plane;
-    B2D_CUDA(cudaMemcpyAsync(h->d_x_stage, x_inout_host, n * 4, cudaMemcpyHostToDevice, st));
-    // conditioning staging (freed with the handle; sized on first use)
-    float *d_lsm = nullptr, *d_topo = nullptr, *d_cond = nullptr;
-    int64_t* d_y = nullptr;
-    std::vector<void*> tmp;
-    auto stage = [&](const void* src, size_t bytes, void** dst) -> int {
-        if (!src) return 0;
-        B2D_CUDA(cudaMalloc(dst, bytes));
-        tmp.push_back(*dst);
-        B2D_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, st));
-        return 0;
-    };
-    int rc = 0;
-    do {
-        if ((rc = stage(lsm_host, (size_t)B * plane * 4, (void**)&d_lsm))) break;
-        if ((rc = stage(topo_host, (size_t)B * plane * 4, (void**)&d_topo))) break;
-        const size_t cond_elems = (c.family == B2D_FAMILY_D) ? (size_t)B * c.cond_channels * cond_h * cond_w
-                                                             : (size_t)B * c.cond_channels * plane;
-        if ((rc = stage(cond_host, cond_elems * 4, (void**)&d_cond))) break;
-        if ((rc = stage(y_host, (size_t)B * 8, (void**)&d_y))) break;
-        if (noise_host) {
-            const size_t ne = (size_t)h->T * n;
-            if (ne > h->noise_stage_elems) {
-                if ((rc = h->alloc(&h->d_noise_stage, ne))) break;
-                h->noise_stage_elems = ne;
-            }
-            if (cudaMemcpyAsync(h->d_noise_stage, noise_host, ne * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-                rc = fail(-2, "noise upload failed");
-                break;
-            }
-        }
-        if ((rc = b2d_set_conditioning(h, d_lsm, d_topo, d_cond, cond_h, cond_w, d_y, B, st))) break;
-        if ((rc = b2d_sample(h, h->d_x_stage, noise_host ? h->d_noise_stage : nullptr, seed, sample_offset, noise_scale, B, st)))
-            break;
-        if (cudaMemcpyAsync(x_inout_host, h->d_x_stage, n * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
-            rc = fail(-2, "result download failed");
-            break;
-        }
-    } while (0);
+    const int rc = sample_host_enqueue(h, x_inout_host, lsm_host, topo_host, cond_host, cond_h, cond_w, y_host, noise_host, seed,
+                                       sample_offset, noise_scale, B, st);
     cudaError_t se = cudaStreamSynchronize(st);
-    for (void* p : tmp) cudaFree(p);
     if (rc) return rc;
     B2D_CUDA(se);
     return 0;
@@ -1343,8 +1257,6 @@ int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32
                      int32_t max_ops, int32_t* n_ops) {
     B2D_CHECK(h && x && t_host && out && n_ops && reps >= 1, "bad argument");
     B2D_TRY(ensure_program(h, B));
-    if (!h->kids.empty())   // split handle: profile the first sub-batch's program (its launches carry its own work figures)
-        return b2d_profile_step(static_cast<b2d_handle*>(h->kids[0]), x, t_host, h->kid_B[0], reps, out, max_ops, n_ops);
     cudaStream_t st = h->own_stream;
     std::vector<int> ti(B);
     for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
@@ -1386,7 +1298,6 @@ int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32
 
 int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out) {
     B2D_CHECK(h && name && out_host, "null argument");
-    if (!h->kids.empty()) return fail(-1, "debug taps are only available on unsplit programs (batch < 16 or B2D_SPLIT=1)");
     auto it = h->taps.find(name);
     if (it == h->taps.end()) return fail(-3, std::string("no such tap: ") + name);
     const size_t n = (size_t)h->prog_B * it->second.hw * it->second.hw * it->second.C;
@@ -1520,21 +1431,40 @@ int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t v
 int b2d_op_posterior_update(float* x, const float* eps, const float* z, const float* betas, const float* alphas,
                             const float* alpha_hat, int32_t i, int32_t B, int64_t per_sample, uint64_t seed,
                             uint64_t sample_offset, float noise_scale, void* stream) {
+    B2D_CHECK(x && eps && betas && alphas && alpha_hat && B >= 1 && per_sample >= 1, "bad argument");
+    B2D_CHECK(per_sample % 4 == 0, "per-sample element count must be a multiple of 4 (vectorised update)");
     cudaStream_t st = as_stream(stream);
-    int* d_step = nullptr;
-    B2D_CUDA(cudaMalloc(&d_step, 16));
-    B2D_CUDA(launch_k(fill_int_kernel, dim3(1), dim3(32), 0, st, d_step, i, 1));
+    // persistent scratch of this entry point (step index + job block): no allocation or synchronisation per call
+    struct Scratch { int* step = nullptr; SampleJob* job = nullptr; };
+    static thread_local Scratch sc;
+    if (!sc.step) {
+        B2D_CUDA(cudaMalloc(&sc.step, 16));
+        B2D_CUDA(cudaMalloc(&sc.job, sizeof(SampleJob)));
+    }
     const size_t n = (size_t)B * per_sample;
-    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)148 * 8);
+    SampleJob job{};
     // z (if given) is the noise of THIS step: bias the pointer so that noise + i*n lands on it
-    const float* noise = z ? z - (size_t)i * n : nullptr;
-    B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, x, eps, noise, alphas, betas, alpha_hat, d_step, nullptr, B, n,
-                                                    (size_t)per_sample, seed, sample_offset, noise_scale, n));
-    cudaError_t e = cudaGetLastError();
-    cudaStreamSynchronize(st);
-    cudaFree(d_step);
-    B2D_CUDA(e);
+    job.noise = z ? z - (size_t)i * n : nullptr;
+    job.seed = seed;
+    job.sample_offset = sample_offset;
+    job.noise_stride = n;
+    job.noise_scale = noise_scale;
+    B2D_CUDA(launch_k(set_job_kernel, dim3(1), dim3(32), 0, st, sc.job, job, sc.step + 2, sc.step, (int)i, 0));
+    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)148 * 8);
+    B2D_CUDA(launch_k(posterior_update_kernel, dim3(blocks), dim3(256), 0, st, x, eps, sc.job, alphas, betas, alpha_hat, sc.step, nullptr, B, n,
+                      (size_t)per_sample));
+    B2D_CUDA(cudaGetLastError());
     return 0;
+}
+
+unsigned int b2d_saturation_count(int32_t reset) {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_sat_count, sizeof(v)) != cudaSuccess) return 0xFFFFFFFFu;
+    if (reset) {
+        const unsigned int z = 0;
+        cudaMemcpyToSymbol(g_sat_count, &z, sizeof(z));
+    }
+    return v;
 }
 
 }  // extern "C"

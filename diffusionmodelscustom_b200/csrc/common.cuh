@@ -80,12 +80,17 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// fp32 -> fp16 pair, saturating at +-65504 so that an out-of-range activation can never become inf/NaN
+// fp32 -> fp16 pair, saturating at +-65504 so that an out-of-range activation can never become inf/NaN.  The clamp is the
+// converter's own (F2FP.SATFINITE, one instruction per pair); every clamped pair is COUNTED in g_sat_count so that a
+// checkpoint whose activations leave the fp16 range is noticed instead of silently clipped (b2d_saturation_count()).
 constexpr float F16_MAX = 65504.0f;
+__device__ unsigned int g_sat_count;
 __device__ __forceinline__ float sat_h(float a) { return fminf(fmaxf(a, -F16_MAX), F16_MAX); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    f162 v = __floats2half2_rn(sat_h(a), sat_h(b));
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // low half <- a, high half <- b
+    if (fmaxf(fabsf(a), fabsf(b)) > F16_MAX) atomicAdd(&g_sat_count, 1u);
+    return r;
 }
 __device__ __forceinline__ uint32_t pack_h2_nosat(float a, float b) {   // inputs known to be in [0, 1]
     f162 v = __floats2half2_rn(a, b);

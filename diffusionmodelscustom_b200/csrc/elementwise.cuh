@@ -694,18 +694,41 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
     return make_float2(r * c, r * s);
 }
 
+// Everything a sampling job may change between calls, resident in device memory so that the captured step graphs never
+// depend on it (b2d_sample writes the block with set_job_kernel before the first replay).
+struct SampleJob {
+    const float* noise;                 // host-injected z: [T][noise_stride] indexed by i, or null = in-kernel Philox
+    unsigned long long seed, sample_offset;
+    unsigned long long noise_stride;    // elements per step of `noise`
+    float noise_scale;                  // multiplies z (1.0; 0.005 for data_scaled, src/diffusion_modules.py:173-174)
+    int pad;
+};
+__global__ void set_job_kernel(SampleJob* job, SampleJob v, int* t_arr, int* step_ptr, int i0, int B) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x == 0) {
+        *job = v;
+        step_ptr[0] = i0;
+        step_ptr[1] = 0;
+    }
+    for (int b = threadIdx.x; b < B; b += blockDim.x) t_arr[b] = i0;
+}
+
 // step_ptr[0] holds the current i (device-resident so one captured graph is replayed for every step).
-// t_arr[b] is rewritten to i-1 for the next evaluation.  4 elements per thread.
+// t_arr[b] is rewritten to i-1 for the next evaluation.  4 elements per thread (n % 4 == 0 and per_sample % 4 == 0 are
+// checked by the C entry points).
 __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict__ x, const float* __restrict__ eps,
-                                                               const float* __restrict__ noise,  // [T][n] or null
+                                                               const SampleJob* __restrict__ job,
                                                                const float* __restrict__ alphas, const float* __restrict__ betas,
                                                                const float* __restrict__ alpha_hat, int* __restrict__ step_ptr,
-                                                               int* __restrict__ t_arr, int B, size_t n, size_t per_sample,
-                                                               unsigned long long seed, unsigned long long sample_offset,
-                                                               float noise_scale, size_t noise_stride) {
+                                                               int* __restrict__ t_arr, int B, size_t n, size_t per_sample) {
     pdl_launch_dependents();
     pdl_wait();
     const int i = *step_ptr;
+    const float* noise = job->noise;
+    const unsigned long long seed = job->seed, sample_offset = job->sample_offset;
+    const size_t noise_stride = job->noise_stride;
+    const float noise_scale = job->noise_scale;
     const float alpha = alphas[i], beta = betas[i], ahat = alpha_hat[i];
     const float c1 = __fdiv_rn(1.0f, __fsqrt_rn(alpha));
     const float c2 = __fdiv_rn(__fsub_rn(1.0f, alpha), __fsqrt_rn(__fsub_rn(1.0f, ahat)));
@@ -716,8 +739,10 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
         const float4 ev = reinterpret_cast<const float4*>(eps)[v];
         float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i > 1) {
-            if (noise) {
-                zv = reinterpret_cast<const float4*>(noise + (size_t)i * noise_stride)[v];   // noise_stride = elements per step
+            if (noise) {   // injected z stands in for randn_like's output: the data_scaled factor applies to it too (:173-174)
+                zv = reinterpret_cast<const float4*>(noise + (size_t)i * noise_stride)[v];
+                zv = make_float4(__fmul_rn(zv.x, noise_scale), __fmul_rn(zv.y, noise_scale), __fmul_rn(zv.z, noise_scale),
+                                 __fmul_rn(zv.w, noise_scale));
             } else {
                 const size_t e = v * 4;
                 const unsigned long long sample = sample_offset + e / per_sample;

@@ -177,6 +177,7 @@ class NativeModel(nn.Module):
         self._cond_key = None
         self._sched_key = None
         self._max_batch = 0
+        self._refresh_epoch = 0
         self.debug_simt_conv = False
 
     # -- to be provided by subclasses
@@ -184,8 +185,32 @@ class NativeModel(nn.Module):
         raise NotImplementedError
 
     def _weights_version(self):
-        return tuple(int(t._version) for t in list(self.parameters()) + list(self.buffers())) + \
-            tuple(t.data_ptr() for t in self.parameters())
+        """Identity of the parameter set the native handle was packed from.  ``tensor._version`` misses in-place writes through
+        ``.data`` (``m.bias.data.fill_()``, EMA updates — the reference's own scripts do both), so the key also carries a CONTENT
+        fingerprint: the L2 norm of every floating-point parameter/buffer (a handful of fused ``_foreach_norm`` kernels and one
+        small D2H copy per call).  ``refresh_weights()`` forces a re-pack explicitly."""
+        ts = [t for t in list(self.parameters()) + list(self.buffers()) if t.dtype.is_floating_point and t.numel() > 0]
+        ident = tuple(int(t._version) for t in ts) + tuple(t.data_ptr() for t in ts) + (self._refresh_epoch,)
+        if not ts:
+            return ident
+        fp = torch.stack(torch._foreach_norm([t.detach() for t in ts])).to("cpu", torch.float64)
+        return ident + (fp.numpy().tobytes(),)
+
+    def refresh_weights(self):
+        """Drop the native handle so that the next call re-packs the current parameter values (use after any weight update the
+        automatic detection could miss)."""
+        self._refresh_epoch += 1
+        self._release()
+
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self.refresh_weights()
+        return r
+
+    @staticmethod
+    def saturation_count(reset: bool = False) -> int:
+        """fp32->fp16 conversions clamped at +-65504 since the last reset (0 = the fp16 activation storage never clipped)."""
+        return int(N.lib().b2d_saturation_count(int(reset)))
 
     def _release(self):
         if self._h is not None:
@@ -303,7 +328,9 @@ class DiffusionNet(NativeModel):
         if key != self._cond_key:
             N.check(N.lib().b2d_set_conditioning(h, N.ptr(lsm), N.ptr(topo), N.ptr(cond), 0, 0, N.ptr(yy), B, stream))
             self._cond_key = key
-            self._cond_refs = (lsm, topo, cond, yy)   # keep staging copies alive until consumed
+            # keep the staging copies alive until consumed AND the caller's tensors alive while they key the cache: a freed
+            # original's address can be recycled by the caching allocator for the next batch (same ptr/version/shape)
+            self._cond_refs = (lsm, topo, cond, yy, lsm_cond, topo_cond, cond_img, y)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None,
@@ -340,14 +367,6 @@ class DiffusionNet(NativeModel):
             if nz is not None:
                 torch.cuda.current_stream().synchronize()   # nz staging copy must outlive the queued work
         return x
-
-
-    def _set_schedule(self, h, betas, alphas, alpha_hat):
-        skey = (betas.data_ptr(), int(betas._version), len(betas))
-        if skey != self._sched_key:
-            b, a, ah = (v.detach().to("cpu", torch.float32).contiguous() for v in (betas, alphas, alpha_hat))
-            N.check(N.lib().b2d_set_schedule(h, b.data_ptr(), a.data_ptr(), ah.data_ptr(), len(b)))
-            self._sched_key = skey
 
     @torch.no_grad()
     def native_sample_host(self, x_host, y, cond_img, lsm_cond, topo_cond, betas, alphas, alpha_hat, device, noise=None,

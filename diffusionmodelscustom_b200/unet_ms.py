@@ -100,7 +100,7 @@ class UNet_downscale(NativeModel):
             ch, cw = (0, 0) if lowc is None else (lowc.shape[-2], lowc.shape[-1])
             N.check(N.lib().b2d_set_conditioning(h, None, None, N.ptr(lowc), ch, cw, None, B, stream))
             self._cond_key = key
-            self._cond_refs = (lowc,)
+            self._cond_refs = (lowc, low)   # the original too: its address keys the cache and must not be recycled
 
     def _bind(self, x):
         c_hr = x.shape[1]

@@ -84,7 +84,9 @@ int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps
 /* Whole reverse loop i = T-1 .. 1 on device memory (DiffusionUtils.sample, diffusion_DANRA_conditional.py:127-157).
  * x_inout: device fp32 [B,c_hr,H,W], x_T in / x_0 out.  noise: device fp32 [T][B*c_hr*H*W] host-generated z_i indexed by
  * i (parity runs) or NULL for in-kernel Philox keyed by (seed, sample_offset + sample index, i).
- * noise_scale multiplies z (1.0; 0.005 for data_scaled, src/diffusion_modules.py:173-174). */
+ * noise_scale multiplies z — drawn or injected — (1.0; 0.005 for data_scaled, src/diffusion_modules.py:173-174).
+ * The handle captures its step graphs once per (batch, schedule length): seed, offset, scale, the noise pointer and the state
+ * live in device memory, so repeated jobs replay the same graphs (x_inout is copied into / out of the handle's state buffer). */
 int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed, uint64_t sample_offset,
                float noise_scale, int32_t B, void* stream);
 
@@ -92,6 +94,11 @@ int b2d_sample(b2d_handle* h, float* x_inout, const float* noise, uint64_t seed,
 int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, const float* topo_host,
                     const float* cond_host, int32_t cond_h, int32_t cond_w, const int64_t* y_host,
                     const float* noise_host, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B);
+
+/* fp32 -> fp16 conversions that had to be clamped to +-65504 since the last reset (all handles of this process/device).
+ * Activations are stored in fp16; a non-zero count means the loaded checkpoint leaves that range somewhere and the
+ * result is clipped there.  Returns 0xFFFFFFFF on a CUDA error. */
+unsigned int b2d_saturation_count(int32_t reset);
 
 /* Kernel launches issued by the last b2d_forward / b2d_sample on this handle (graph nodes x replays). */
 int64_t b2d_last_launch_count(const b2d_handle* h);

@@ -1,7 +1,8 @@
 """GPU parity of the whole path through the reference-facing API (drop-in classes -> C ABI -> CUDA kernels).
 
-Gates (BASELINE.md §5 / north_star): per-step eps_hat relative L2 <= 1e-2 (bf16 tensor-core path vs the FP32 reference);
-free-running final sample RMSE <= 5e-2 * std of the reference field.  References: the committed golden fixtures produced by
+Gates: per-step eps_hat relative L2 <= 3e-3 (north_star allows 1e-2 for BF16/TF32 vs the FP32 reference; the fp16-operand path
+achieves ~1e-3, and the tighter gate is needed to catch e.g. a wrong per-level time projection at 128x128, whose effect is
+only 2.9e-2); free-running final sample RMSE <= 5e-2 * std of the reference field; no fp16 saturation anywhere.  References: the committed golden fixtures produced by
 the unmodified reference, and the CPU oracle (pinned to those fixtures) for shapes the fixtures do not cover."""
 import os
 
@@ -12,11 +13,13 @@ import torch
 from diffusionmodelscustom_b200 import DiffusionUtils, synth
 from oracle import ddpm_oracle as O
 from tests import gpu_util as G
+from diffusionmodelscustom_b200 import DiffusionUtilsV2
+from diffusionmodelscustom_b200.modules import NativeModel
 from tests.cases import D_CASES, R_CASES, SAMPLE_CASES
 from tests.model_util import build_ours_d, build_ours_r, inputs_d, inputs_r
 
 pytestmark = pytest.mark.gpu
-EPS_TOL = 1e-2
+EPS_TOL = 3e-3
 RMSE_TOL = 5e-2
 
 
@@ -26,11 +29,48 @@ def test_family_r_eps_vs_reference_golden(name, golden_dir):
     gold = np.load(os.path.join(golden_dir, f"r_{name}.npz"))
     net, _ = build_ours_r(case)
     inp, dev = inputs_r(case)
+    NativeModel.saturation_count(reset=True)
     for t in case["ts"]:
         tt = torch.full((case["batch"],), t, dtype=torch.long, device="cuda")
         eps = net(dev["x"] * case.get("x_scale", 1.0), tt, dev["y"], dev["cond"], dev["lsm"], dev["topo"])
         err = G.rel_l2(eps, gold[f"eps_t{t}"])
         assert err < EPS_TOL, (name, t, err)
+    assert NativeModel.saturation_count() == 0, "fp16 activation storage clipped"
+
+
+# The programs that bench.py times.  The batch SELECTS kernels (LN-folded streaming GEMM needs >= 8192 rows, split-K cluster
+# width, norm cluster width, samples per attention-block CTA, GroupNorm quarter partials), so the full program is run at the
+# benchmarked per-GPU batch and — samples being independent — rows {0, B/2, B-1} are checked against the
+# oracle evaluated on exactly those samples.
+BENCH_PROGRAMS = [("cfg2_lsmtopo_64", 64), ("cfg3_full_128", 32), ("cfg3_full_128", 256), ("cfg5_flexible_128", 128),
+                  ("cfg4_downscale_64", 64)]
+
+
+@pytest.mark.parametrize("name,batch", BENCH_PROGRAMS)
+def test_full_program_at_bench_batch_vs_oracle(name, batch):
+    rows = [0, batch // 2, batch - 1]
+    g = torch.Generator().manual_seed(5)
+    t = torch.randint(1, 1000, (batch,), generator=g)
+    t[0], t[-1] = 999, 1
+    NativeModel.saturation_count(reset=True)
+    if name in D_CASES:
+        case = dict(D_CASES[name], iseed=61)
+        net, sd = build_ours_d(case)
+        inp, dev = inputs_d(case, batch)
+        eps = net(dev["x"], t.cuda(), dev["y_lowres"])
+        ref = O.family_d_forward(sd, inp["x"][rows], t[rows], inp["y_lowres"][rows])
+    else:
+        case = dict(R_CASES[name], iseed=61)
+        net, sd = build_ours_r(case)
+        inp, dev = inputs_r(case, batch)
+        eps = net(dev["x"], t.cuda(), dev["y"], dev["cond"], dev["lsm"], dev["topo"])
+        pick = lambda v: None if v is None else v[rows]
+        ref = O.family_r_forward(sd, inp["x"][rows], t[rows], pick(inp["y"]), pick(inp["cond"]), pick(inp["lsm"]), pick(inp["topo"]))
+    assert torch.isfinite(eps).all()
+    for k, r in enumerate(rows):
+        err = G.rel_l2(eps[r], ref[k])
+        assert err < EPS_TOL, (name, batch, r, int(t[r]), err)
+    assert NativeModel.saturation_count() == 0
 
 
 def test_family_r_eps_vs_oracle_batch5_mixed_t():
@@ -143,6 +183,101 @@ def test_errors_are_python_exceptions():
         net(dev["x"], tt, None, None, None, dev["topo"])          # lsm required by construction
     with pytest.raises(RuntimeError):
         net(inp["x"], tt.cpu())                                   # CPU tensors: no fallback
+
+
+def _free_running(name, golden_dir, tol=RMSE_TOL):
+    sc = SAMPLE_CASES[name]
+    path = os.path.join(golden_dir, f"sample_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip(f"golden fixture {name} not generated")
+    gold = np.load(path)["x0"]
+    B, T = sc["batch"], sc["T"]
+    if sc.get("family") == "D":
+        case = D_CASES[sc["model"]]
+        net, _ = build_ours_d(case)
+        inp, dev = inputs_d(case, B)
+        kw = dict(cond_img=dev["y_lowres"])
+    else:
+        case = R_CASES[sc["model"]]
+        net, _ = build_ours_r(case)
+        inp, dev = inputs_r(case, B)
+        kw = dict(y=dev["y"], cond_img=dev["cond"], lsm_cond=dev["lsm"], topo_cond=dev["topo"])
+    z = synth.step_noise(B, 1, case["hw"], T, seed=sc["zseed"]).cuda()
+    NativeModel.saturation_count(reset=True)
+    if sc.get("v2"):
+        du = DiffusionUtilsV2(T, 1e-4, 0.02, "cuda", sc.get("scheduler", "linear"), img_size=case["hw"],
+                              data_scaled=sc.get("data_scaled", False))
+        x_T = dev["x"] * (0.005 if sc.get("data_scaled") else 1.0)      # src/diffusion_modules.py:134-137
+        x0 = du.sample(B, net, 1, x_T=x_T, noise=z, **kw)
+        assert net.training                                             # the v2 sampler leaves the model in train mode (:182)
+    else:
+        du = DiffusionUtils(T, 1e-4, 0.02, "cuda", sc.get("scheduler", "linear"))
+        x0 = du.sample(dev["x"], net, noise=z, **kw)
+    np.testing.assert_array_equal(du.betas.cpu().numpy(), np.load(path)["betas"])      # schedule tables are bit-identical
+    assert torch.isfinite(x0).all()
+    rmse = float((x0.cpu() - torch.from_numpy(gold)).pow(2).mean().sqrt())
+    return rmse, float(gold.std()), NativeModel.saturation_count()
+
+
+@pytest.mark.parametrize("name", ["v1_cosine_T30", "v2_scaled_T40", "cfg4_T200", "cfg3_T1000"])
+def test_free_running_variants_vs_reference_golden(name, golden_dir):
+    """v1 raised-cosine schedule; v2 sampler with data_scaled noise; Family D over 199 steps; 128x128 over the full T=1000."""
+    rmse, sigma, sat = _free_running(name, golden_dir)
+    assert rmse <= RMSE_TOL * sigma, (name, rmse, sigma)
+    assert sat == 0
+
+
+def test_v2_cosine_schedule_blow_up_is_reported_not_hidden(golden_dir):
+    """Nichol-Dhariwal cosine betas reach 0.9999: with random weights the reference's own x_0 grows to |x| ~ 3e4 (std 3.7e3).
+    Either the native path still matches the reference, or the fp16 activation storage clipped and the saturation counter
+    says so — silent divergence is the one outcome that is not allowed."""
+    rmse, sigma, sat = _free_running("v2_cosine_scaled_T40", golden_dir)
+    assert rmse <= RMSE_TOL * sigma or sat > 0, (rmse, sigma, sat)
+
+
+def test_graphs_follow_schedule_length_and_label_presence():
+    """the cached step graphs must not survive a change of T (new tables) or of y on/off (time-embedding input)."""
+    case = R_CASES["full_64_randbn"]
+    net, sd = build_ours_r(case)
+    inp, dev = inputs_r(case, 2)
+    for T, use_y in ((50, True), (12, True), (12, False), (50, True)):
+        y_d, y_h = (dev["y"], inp["y"]) if use_y else (None, None)
+        z = synth.step_noise(2, 1, case["hw"], T, seed=9)
+        x0 = DiffusionUtils(T, 1e-4, 0.02, "cuda").sample(dev["x"], net, y_d, dev["cond"], dev["lsm"], dev["topo"], noise=z.cuda(), seed=3)
+        fn = lambda x, tt: O.family_r_forward(sd, x, tt, y_h, inp["cond"], inp["lsm"], inp["topo"])
+        ref = O.sample(fn, inp["x"].clone(), T, 1e-4, 0.02, noise=z)
+        rmse = float((x0.cpu() - ref).pow(2).mean().sqrt())
+        assert rmse <= RMSE_TOL * float(ref.std()), (T, use_y, rmse)
+
+
+def test_conditioning_cache_is_not_fooled_by_recycled_addresses():
+    """float64 / non-contiguous conditioning is staged to fp32 copies; the cache key must not match a NEW batch whose
+    temporaries happen to land on the freed addresses."""
+    case = R_CASES["cfg2_lsmtopo_64"]
+    net, sd = build_ours_r(case)
+    tt = torch.full((2,), 300, dtype=torch.long)
+    outs = []
+    for seed in (7, 8):
+        inp, _ = inputs_r(dict(case, iseed=seed), 2)
+        lsm64, topo64 = inp["lsm"].double().cuda(), inp["topo"].double().cuda()
+        eps = net(inp["x"].cuda(), tt.cuda(), None, None, lsm64, topo64)
+        ref = O.family_r_forward(sd, inp["x"], tt, None, None, inp["lsm"], inp["topo"])
+        assert G.rel_l2(eps, ref) < EPS_TOL, seed
+        del lsm64, topo64
+        outs.append(eps)
+
+
+def test_in_place_data_update_is_detected():
+    """p.data.fill_() does not bump tensor._version; the content fingerprint must still trigger a re-pack."""
+    case = R_CASES["cfg1_uncond_64"]
+    net, _ = build_ours_r(case)
+    inp, dev = inputs_r(case)
+    tt = torch.full((case["batch"],), 10, dtype=torch.long, device="cuda")
+    a = net(dev["x"], tt).clone()
+    old = float(net.decoder.final_layer.conv.bias.data[0])
+    net.decoder.final_layer.conv.bias.data.fill_(old + 0.75)      # the reference's scripts write weights like this
+    b = net(dev["x"], tt)
+    assert abs(float((b - a).mean()) - 0.75) < 1e-2
 
 
 # ----------------------------------------------------------------------------------------------- Family D (cfg 4)

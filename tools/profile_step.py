@@ -9,8 +9,7 @@ import torch
 
 sys.path.insert(0, ".")
 from bench import WORKLOADS                            # noqa: E402
-from tests.cases import D_CASES, R_CASES               # noqa: E402
-from tests.model_util import build_ours_d, build_ours_r, inputs_d, inputs_r    # noqa: E402
+from diffusionmodelscustom_b200.configs import D_CASES, R_CASES, build_ours_d, build_ours_r, inputs_d, inputs_r  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="cfg2")
