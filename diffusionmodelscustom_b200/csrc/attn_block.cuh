@@ -147,8 +147,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     uint32_t okeep[2][16];   // gather mode: this thread's share of O_h (fp16 pairs), alive across the cluster barrier
 #pragma unroll
     for (int i = 0; i < 16; ++i) { okeep[0][i] = 0u; okeep[1][i] = 0u; }
+    // single-thread roles are guarded by elect.sync (not `lane == 0`): ptxas then keeps the operands of the TMA / tcgen05
+    // instructions on the uniform datapath instead of wrapping each one in an ELECT / R2UR.BROADCAST waterfall loop
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % STAGES;
                 mbar_wait(&empty[st], ((kb / STAGES) & 1) ^ 1);
@@ -175,7 +177,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // ---- 1. QKV projection
             constexpr int N1 = (3 * D <= 256) ? 3 * D : 256;
             constexpr uint32_t idesc1 = umma_idesc_f16(128, N1);

@@ -2,6 +2,7 @@
 // Family R (DiffusionNet) and the CUDA-graph sampling loop.  Host orchestration only; all arithmetic is in the kernels.
 #include "../../include/b200ddpm.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <functional>
@@ -11,10 +12,13 @@
 
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_tc2.cuh"
+#include "attention_tc3.cuh"
 #include "attn_block.cuh"
 #include "common.cuh"
 #include "conv.cuh"
 #include "elementwise.cuh"
+#include "evalops.cuh"
 #include "gemm_stream.cuh"
 #include "norm_fused.cuh"
 
@@ -63,6 +67,8 @@ struct OpList {
     }
 };
 
+struct EnsembleRes;
+void ensemble_release(EnsembleRes* r);
 struct Handle {
     b2d_config cfg{};
     int num_sms = 148;
@@ -107,6 +113,7 @@ struct Handle {
     float *d_lsm_stage = nullptr, *d_topo_stage = nullptr, *d_cond_stage = nullptr;
     size_t cond_stage_elems = 0;
     int* h_y_pinned = nullptr;       // pinned int32 labels for the host entry
+    struct EnsembleRes* ens = nullptr;   // double-buffered staging of the ensemble driver (ensemble.cuh), created on first use
     int64_t last_launches = 0;
     cudaStream_t own_stream = nullptr;
     // Time-embedding pipelining inside the reverse loop: d_temb depends on the step index only, so the projections for
@@ -149,6 +156,7 @@ struct Handle {
     }
     ~Handle() {
         drop_graphs();
+        ensemble_release(ens);
         if (h_y_pinned) cudaFreeHost(h_y_pinned);
         free_program();
         for (void* p : allocs) cudaFree(p);
@@ -541,7 +549,20 @@ struct Builder {
             auto tmq = std::make_shared<AttnTcMaps>();
             if (attn_tc_make_map(tmq.get(), qkv, B, L, C) != 0) { err = -1; return; }
             ops.meta(role + ".sdpa", "attn_tc", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
-            ops.push_back([=](cudaStream_t st) { return attn_tc_launch(*tmq, ao, Bc, L, C, heads, st); });
+            // B2D_ATTN_V=1: round-1 kernel (3 CTAs/SM); 2: persistent two-tile kernel (attention_tc2.cuh); default 3: the
+            // four-CTAs-per-SM optimistic-maximum kernel (attention_tc3.cuh) — A/B switches, all three are parity-tested
+            static const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 3;
+            const int sms = h->num_sms;
+            if (attn_v == 2 && attn_tc2_supported(L, C, heads))
+                ops.push_back([=](cudaStream_t st) { return attn_tc2_launch(*tmq, ao, Bc, L, C, heads, sms, st); });
+            else if (attn_v == 1)
+                ops.push_back([=](cudaStream_t st) { return attn_tc_launch(*tmq, ao, Bc, L, C, heads, st); });
+            else if (attn_v == 4) {
+                auto tm4 = std::make_shared<AttnTcMaps>();
+                if (attn_tc4_make_map(tm4.get(), qkv, B, L, C) != 0) { err = -1; return; }
+                ops.push_back([=](cudaStream_t st) { return attn_tc4_launch(*tm4, ao, Bc, L, C, heads, st); });
+            } else
+                ops.push_back([=](cudaStream_t st) { return attn_tc3_launch(*tmq, ao, Bc, L, C, heads, st); });
         } else {
             ops.meta(role + ".sdpa", "flash_attn", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
             ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
@@ -809,6 +830,11 @@ static int init_uniform_carveout() {
     B2D_TRY(set_carveout(attn_small_d_kernel<4>));
     B2D_TRY(set_carveout(attn_small_d_kernel<8>));
     B2D_TRY(set_carveout(attn_tc_kernel));
+    B2D_TRY(set_carveout(attn_tc2_kernel<0>));
+    B2D_TRY(set_carveout(attn_tc2_kernel<1>));
+    B2D_TRY(set_carveout(attn_tc2_kernel<2>));
+    B2D_TRY(set_carveout(attn_tc2_kernel<3>));
+    B2D_TRY(set_carveout(attn_tc2_kernel<4>));
     B2D_TRY(set_carveout(temb_project_kernel));
     B2D_TRY(set_carveout(stem_conv_kernel<8, 2>));
     B2D_CUDA(cudaFuncSetAttribute(stem_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_MMA_SMEM));
@@ -960,6 +986,8 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = conv_tc_init_attrs())) break;
         if ((rc = flash_attn_init_attrs())) break;
         if ((rc = attn_tc_init_attrs())) break;
+        if ((rc = attn_tc2_init_attrs())) break;
+        if ((rc = attn_tc3_init_attrs())) break;
         if ((rc = gemm_stream_init_attrs())) break;
         if ((rc = attn_block_init_attrs())) break;
         if ((rc = norm_fused_init_attrs())) break;
@@ -1040,13 +1068,17 @@ int b2d_set_schedule(b2d_handle* h, const float* betas, const float* alphas, con
 // y_dev: int64 labels in device memory (synchronises once to range-check them, as nn.Embedding would raise);
 // y_host: the same in host memory (no device round trip).  At most one of them is non-null.
 static int set_conditioning_impl(b2d_handle* h, const float* lsm, const float* topo, const float* cond, int32_t cond_h,
-                                 int32_t cond_w, const int64_t* y_dev, const int64_t* y_host, int32_t B, cudaStream_t st) {
+                                 int32_t cond_w, const int64_t* y_dev, const int64_t* y_host, int32_t B, cudaStream_t st,
+                                 const int* y_dev_i32 = nullptr /* already range-checked int32 labels in device memory */) {
     B2D_CHECK(h, "null handle");
     B2D_TRY(ensure_program(h, B));
     const b2d_config& c = h->cfg;
     const int H = c.img_size;
-    const bool has_y = (y_dev != nullptr || y_host != nullptr);
-    if (has_y) {
+    const bool has_y = (y_dev != nullptr || y_host != nullptr || y_dev_i32 != nullptr);
+    if (y_dev_i32) {
+        B2D_CHECK(c.num_classes > 0, "y given but the model has no label embedding");
+        B2D_CUDA(cudaMemcpyAsync(h->d_y, y_dev_i32, B * 4, cudaMemcpyDeviceToDevice, st));
+    } else if (has_y) {
         B2D_CHECK(c.num_classes > 0, "y given but the model has no label embedding");
         std::vector<int64_t> tmp;
         if (y_dev) {
@@ -1251,6 +1283,8 @@ int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, c
     return 0;
 }
 
+#include "ensemble.cuh"
+
 int64_t b2d_last_launch_count(const b2d_handle* h) { return h ? h->last_launches : 0; }
 
 int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32_t B, int32_t reps, b2d_op_profile* out,
@@ -1371,6 +1405,23 @@ int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, 
         B2D_TRY(attn_tc_init_attrs());
         AttnTcMaps tm;
         B2D_TRY(attn_tc_make_map(&tm, (const f16*)qkv, B, L, C));
+        const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 3;
+        if (attn_v == 3) {
+            B2D_TRY(attn_tc3_init_attrs());
+            return attn_tc3_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
+        }
+        if (attn_v == 4) {
+            B2D_TRY(attn_tc3_init_attrs());
+            B2D_TRY(attn_tc4_make_map(&tm, (const f16*)qkv, B, L, C));
+            return attn_tc4_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
+        }
+        if (attn_v == 2 && attn_tc2_supported(L, C, heads)) {
+            B2D_TRY(attn_tc2_init_attrs());
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            return attn_tc2_launch(tm, (f16*)o, B, L, C, heads, sms, as_stream(stream));
+        }
         return attn_tc_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
     }
     return flash_attn_launch((const f16*)qkv, (f16*)o, B, L, C, heads, as_stream(stream));
@@ -1455,6 +1506,68 @@ int b2d_op_posterior_update(float* x, const float* eps, const float* z, const fl
                       (size_t)per_sample));
     B2D_CUDA(cudaGetLastError());
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ forward process / loss / evaluation
+int b2d_op_noise_image(const float* x0, const int64_t* t_dev, const float* alpha_hat, const float* noise_or_null, float* x_t,
+                       float* noise_out, int32_t B, int64_t per_sample, uint64_t seed, uint64_t sample_offset, float noise_scale,
+                       void* stream) {
+    B2D_CHECK(x0 && t_dev && alpha_hat && x_t && noise_out && B >= 1 && per_sample >= 1, "bad argument");
+    B2D_CHECK(per_sample % 4 == 0, "per-sample element count must be a multiple of 4 (vectorised pass)");
+    const size_t n = (size_t)B * per_sample;
+    const int blocks = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)148 * 8);
+    noise_image_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x0, reinterpret_cast<const long long*>(t_dev), alpha_hat, noise_or_null, x_t,
+                                                               noise_out, n, (size_t)per_sample, seed, sample_offset, noise_scale);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_op_weighted_mse(const float* input, const float* target, const float* sdf_or_null, float max_land_weight,
+                        float min_sea_weight, float* out_scalar_dev, int64_t n, void* stream) {
+    B2D_CHECK(input && target && out_scalar_dev && n >= 1, "bad argument");
+    static thread_local double* partial = nullptr;       // persistent scratch: no allocation per call
+    if (!partial) B2D_CUDA(cudaMalloc(&partial, WMSE_BLOCKS * sizeof(double)));
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, WMSE_BLOCKS);
+    cudaStream_t st = as_stream(stream);
+    weighted_mse_partial_kernel<<<blocks, 256, 0, st>>>(input, target, sdf_or_null, max_land_weight - min_sea_weight, min_sea_weight,
+                                                         partial, (size_t)n);
+    weighted_mse_final_kernel<<<1, 256, 0, st>>>(partial, blocks, 1.0 / (double)n, out_scalar_dev);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_op_eval_daily(const float* gen, const float* eval, float* mae_out, float* rmse_out, int32_t n_samples, int64_t hw,
+                      void* stream) {
+    B2D_CHECK(gen && eval && mae_out && rmse_out && n_samples >= 1 && hw >= 1, "bad argument");
+    eval_daily_kernel<<<n_samples, 256, 0, as_stream(stream)>>>(gen, eval, mae_out, rmse_out, (size_t)hw);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_op_eval_pixel(const float* gen, const float* eval, float* mae_out, float* rmse_out, float* bias_out, int32_t n_samples,
+                      int64_t hw, void* stream) {
+    B2D_CHECK(gen && eval && mae_out && rmse_out && bias_out && n_samples >= 1 && hw >= 1, "bad argument");
+    eval_pixel_kernel<<<(unsigned)((hw + 255) / 256), 256, 0, as_stream(stream)>>>(gen, eval, mae_out, rmse_out, bias_out, n_samples, (size_t)hw);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_op_histogram(const float* x, int64_t n, float lo, float hi, int32_t bins, unsigned long long* counts_dev, void* stream) {
+    B2D_CHECK(x && counts_dev && n >= 0 && bins >= 1 && bins <= HIST_MAX_BINS && hi > lo, "bad argument");
+    cudaStream_t st = as_stream(stream);
+    B2D_CUDA(cudaMemsetAsync(counts_dev, 0, (size_t)bins * 8, st));
+    if (n == 0) return 0;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 4);
+    histogram_kernel<<<blocks, 256, (size_t)bins * 4, st>>>(x, (size_t)n, lo, hi, bins, counts_dev);
+    B2D_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b2d_debug_attn_trace(long long* out_host, int32_t max_elems) {
+    B2D_CHECK(out_host && max_elems >= AT2_TRACE_BLOCKS * 12, "trace buffer too small");
+    B2D_CUDA(cudaDeviceSynchronize());
+    B2D_CUDA(cudaMemcpyFromSymbol(out_host, g_at2_trace, sizeof(long long) * AT2_TRACE_BLOCKS * 12));
+    return AT2_TRACE_BLOCKS;
 }
 
 unsigned int b2d_saturation_count(int32_t reset) {

@@ -72,6 +72,21 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- small device helpers
+// one thread of the (converged) warp, chosen by the hardware: ptxas treats a region guarded by elect.sync as single-threaded and
+// keeps warp-uniform operands of tcgen05 instructions on the uniform datapath (a `lane == 0` guard makes it emit an
+// ELECT / R2UR.BROADCAST waterfall loop per instruction, ~100 clk each)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -779,6 +779,24 @@ __global__ void __launch_bounds__(256) posterior_update_kernel(float* __restrict
         }
     }
 }
+// x_T ~ N(0,1) * scale drawn on the device (ensemble driver): same Philox keying as the per-step noise — (seed; global sample
+// index, element) — with the step slot set to 0x7FFFFFFF, which no reverse step uses, so members are independent of how the
+// ensemble is cut into sub-batches and ranks.
+__global__ void __launch_bounds__(256) init_noise_kernel(float* __restrict__ x, size_t n, size_t per_sample, unsigned long long seed,
+                                                         unsigned long long sample_offset, float scale) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t n4 = n >> 2;
+    for (size_t v = blockIdx.x * (size_t)blockDim.x + threadIdx.x; v < n4; v += (size_t)gridDim.x * blockDim.x) {
+        const size_t e = v * 4;
+        const unsigned long long sample = sample_offset + e / per_sample;
+        const unsigned long long within = (e % per_sample) >> 2;
+        uint32_t c[4] = {(uint32_t)within, 0x7FFFFFFFu, (uint32_t)sample, (uint32_t)(sample >> 32)};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float2 g0 = box_muller(c[0], c[1]), g1 = box_muller(c[2], c[3]);
+        reinterpret_cast<float4*>(x)[v] = make_float4(g0.x * scale, g0.y * scale, g1.x * scale, g1.y * scale);
+    }
+}
 __global__ void fill_int_kernel(int* p, int v, int n) {
     pdl_launch_dependents();
     pdl_wait();

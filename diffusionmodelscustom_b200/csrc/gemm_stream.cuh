@@ -94,30 +94,39 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
     const uint32_t tmem = *tmem_slot;
     pdl_wait();
 
+    // Producer and MMA loops run converged on all 32 lanes, one hardware-elected lane issues (conv.cuh explains why: no
+    // ELECT / R2UR waterfall around every TMA and tcgen05 instruction).
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(b_full, (uint32_t)(KB * NB * 128));
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * NB * 128, &tmB, b_full, kb * 64, nblk * NB);
-            int it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-                const int st = it % STAGES;
-                mbar_wait(&a_empty[st], ((it / STAGES) & 1) ^ 1);
+        }
+        __syncwarp();
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            const int st = it % STAGES;
+            mbar_wait(&a_empty[st], ((it / STAGES) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&a_full[st], KB * CONV_A_BYTES);
                 for (int kb = 0; kb < KB; ++kb)
                     tma_load_2d(sA + (st * KB + kb) * CONV_A_BYTES, &tmA, &a_full[st], kb * 64, t * 128);
-                if (p.residual != nullptr) {
-                    for (int jb = 0; jb < NB / 64; ++jb) {
-                        const int blk = it * (NB / 64) + jb, rb = blk & 1;
-                        mbar_wait(&r_empty[rb], ((blk >> 1) & 1) ^ 1);
+            }
+            __syncwarp();
+            if (p.residual != nullptr) {
+                for (int jb = 0; jb < NB / 64; ++jb) {
+                    const int blk = it * (NB / 64) + jb, rb = blk & 1;
+                    mbar_wait(&r_empty[rb], ((blk >> 1) & 1) ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&r_full[rb], CONV_A_BYTES);
                         tma_load_2d(sR + rb * CONV_A_BYTES, &tmR, &r_full[rb], nblk * NB + jb * 64, t * 128);
                     }
+                    __syncwarp();
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma_idesc_f16(128, NB);
             mbar_wait(b_full, 0);
             int it = 0;
@@ -126,16 +135,19 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
                 mbar_wait(&t_empty[acc], ((it >> 1) & 1) ^ 1);
                 mbar_wait(&a_full[st], (it / STAGES) & 1);
                 tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + (st * KB + kb) * CONV_A_BYTES));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sB + kb * NB * 128));
+                    for (int kb = 0; kb < KB; ++kb) {
+                        const uint64_t da = umma_desc_sw128(smem_u32(sA + (st * KB + kb) * CONV_A_BYTES));
+                        const uint64_t db = umma_desc_sw128(smem_u32(sB + kb * NB * 128));
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem + acc * 256, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem + acc * 256, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&a_empty[st]);
+                    umma_commit(&t_full[acc]);
                 }
-                umma_commit(&a_empty[st]);
-                umma_commit(&t_full[acc]);
+                __syncwarp();
             }
         }
         __syncwarp();

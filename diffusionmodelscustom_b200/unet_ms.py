@@ -54,6 +54,8 @@ class Up(nn.Module):
 
 
 class UNet_downscale(NativeModel):
+    _family = N.FAMILY_D
+
     def __init__(self, c_in=6, c_out=3, time_dim=256, interp_mode='bicubic', img_size=64, device="cuda"):
         super().__init__()
         if time_dim != 256:

@@ -95,6 +95,34 @@ int b2d_sample_host(b2d_handle* h, float* x_inout_host, const float* lsm_host, c
                     const float* cond_host, int32_t cond_h, int32_t cond_w, const int64_t* y_host,
                     const float* noise_host, uint64_t seed, uint64_t sample_offset, float noise_scale, int32_t B);
 
+/* ---- ensemble generation ------------------------------------------------------------------
+ * "dates x members" through the sampler: replaces the host loop around DiffusionUtils.sample in the reference's generation
+ * scripts (generation_DANRA_conditional.py:369-441, DDPM_clean_application/test/generation_ddpm.py:371-439).  The
+ * conditioning fields are given once PER DATE (host memory); the flattened date-major member list [first, first+count) is
+ * sampled in sub-batches with x_T drawn on the device (Philox keyed by the global member index, so the result does not
+ * depend on sub_batch or on how ranks slice the list), uploads / downloads double-buffered on a copy stream. */
+typedef struct b2d_ensemble_job {
+    int32_t n_dates, members, sub_batch;
+    int32_t first, count;      /* slice of the flattened member list this call (this rank) produces */
+    const float* lsm;          /* host [n_dates][H][W] or NULL */
+    const float* topo;         /* host [n_dates][H][W] or NULL */
+    const float* cond;         /* host [n_dates][C][H][W] (Family D: [n_dates][C][cond_h][cond_w]) or NULL */
+    int32_t cond_h, cond_w;    /* Family D low-resolution extent, else 0 */
+    const int64_t* y;          /* host [n_dates] season classes or NULL */
+    float* out;                /* host [count][c_hr][H][W]; page-locked for the call when possible */
+    uint64_t seed;
+    float noise_scale;         /* multiplies z_i (1.0; 0.005 for data_scaled) */
+    float xT_scale;            /* multiplies x_T (1.0; 0.005 for data_scaled, src/diffusion_modules.py:134-137) */
+} b2d_ensemble_job;
+typedef struct b2d_ensemble_stats {
+    int32_t sub_batches;
+    int32_t out_pinned;        /* 1: fields were copied straight into `out`; 0: through the driver's pinned bounce buffers */
+    int64_t launches;
+    double gather_ms;          /* host time spent gathering conditioning rows into the pinned staging */
+    double wall_ms;
+} b2d_ensemble_stats;
+int b2d_ensemble_run(b2d_handle* h, const b2d_ensemble_job* job, b2d_ensemble_stats* stats);
+
 /* fp32 -> fp16 conversions that had to be clamped to +-65504 since the last reset (all handles of this process/device).
  * Activations are stored in fp16; a non-zero count means the loaded checkpoint leaves that range somewhere and the
  * result is clipped there.  Returns 0xFFFFFFFF on a CUDA error. */
@@ -118,6 +146,30 @@ int b2d_profile_step(b2d_handle* h, const float* x, const int64_t* t_host, int32
 /* Bring-up aid: copies a named NHWC f16 activation of the last evaluation ("fmap1".."fmap5", "dec0".."dec3", ...) to
  * host fp32 [B,hw,hw,C]; synchronises the device. */
 int b2d_debug_read(b2d_handle* h, const char* name, float* out_host, int64_t max_elems, int32_t* C_out, int32_t* hw_out);
+
+/* ---- forward process, loss and evaluation statistics; all pointers device memory ------------ */
+/* DiffusionUtils.noiseImage (diffusion_DANRA_conditional.py:85-103): x_t = sqrt(alpha_hat[t]) x_0 + sqrt(1 - alpha_hat[t]) eps, with
+ * eps given (noise_or_null) or drawn in-kernel (Philox keyed by sample_offset + b); eps * noise_scale is written to noise_out
+ * (x0.005 for data_scaled).  t_dev: int64 [B]; alpha_hat: float [T]. */
+int b2d_op_noise_image(const float* x0, const int64_t* t_dev, const float* alpha_hat, const float* noise_or_null, float* x_t,
+                       float* noise_out, int32_t B, int64_t per_sample, uint64_t seed, uint64_t sample_offset, float noise_scale,
+                       void* stream);
+/* SDFWeightedMSELoss.forward (training_DANRA_conditional.py:33-56): mean(w (input - target)^2), w = sigmoid(sdf) (max_land -
+ * min_sea) + min_sea; sdf_or_null == NULL gives nn.MSELoss.  One fused pass, deterministic; scalar written to device memory. */
+int b2d_op_weighted_mse(const float* input, const float* target, const float* sdf_or_null, float max_land_weight,
+                        float min_sea_weight, float* out_scalar_dev, int64_t n, void* stream);
+/* evaluation_DANRA_conditional.py:121-122: per-sample nan-aware MAE and RMSE over the hw pixels of gen/eval [n_samples][hw]. */
+int b2d_op_eval_daily(const float* gen, const float* eval, float* mae_out, float* rmse_out, int32_t n_samples, int64_t hw,
+                      void* stream);
+/* per-pixel nan-aware MAE / RMSE / bias (mean of gen - eval) over the samples; outputs [hw]. */
+int b2d_op_eval_pixel(const float* gen, const float* eval, float* mae_out, float* rmse_out, float* bias_out, int32_t n_samples,
+                      int64_t hw, void* stream);
+/* numpy-style fixed-range histogram (NaN and out-of-range values dropped, right edge closed); counts: uint64 [bins], bins <= 4096. */
+int b2d_op_histogram(const float* x, int64_t n, float lo, float hi, int32_t bins, unsigned long long* counts_dev, void* stream);
+
+/* Bring-up aid: per-key-block clock64 stamps of the persistent attention kernel (only filled by a -DAT2_TRACE build):
+ * [256][12] int64.  Returns the number of rows. */
+int b2d_debug_attn_trace(long long* out_host, int32_t max_elems);
 
 /* ---- single operators (unit-test / profiling entry points; all pointers are device memory) ------------------ */
 /* NHWC f16 convolution / projection through the same kernels the model uses.

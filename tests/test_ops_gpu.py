@@ -140,6 +140,34 @@ def test_attention_matches_torch(case):
     assert G.rel_l2(o.float().cpu(), ref) < 3e-3     # P is rounded to fp16 before P.V
 
 
+# Persistent head_dim-16 kernel (attention_tc2.cuh): several work items per CTA (pipeline running across item boundaries, O
+# read-out / re-initialisation), and PEAKY score distributions (q, k scaled up: row maxima that keep growing across key blocks
+# => lazy-reference moves with O rescaled in TMEM; scores far below the maximum => the packed-half polynomial path must flush
+# to zero exactly like the SFU path).
+ATTN_TC2_CASES = [(37, 1024, 64, 4, 1.0), (3, 1024, 64, 4, 3.0), (2, 4096, 64, 4, 2.5), (1, 256, 64, 4, 4.0), (150, 256, 64, 4, 1.5)]
+
+
+@pytest.mark.parametrize("case", ATTN_TC2_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}_x{s}" for b, l, c, h, s in ATTN_TC2_CASES])
+def test_persistent_attention_items_and_peaky_scores(case):
+    B, L, C, heads, qs = case
+    d = C // heads
+    g = torch.Generator().manual_seed(L + B)
+    qkv = torch.randn(B, L, 3 * C, generator=g)
+    qkv[..., : 2 * C] *= qs
+    qkv = _bf(qkv)
+    qd = qkv.to(torch.float16).cuda()
+    o = torch.full((B, L, C), float("nan"), dtype=torch.float16, device="cuda")
+    N.check(N.lib().b2d_op_attention(qd.data_ptr(), o.data_ptr(), B, L, C, heads, G.stream()))
+    torch.cuda.synchronize()
+    q, k, v = (t.cuda().double().reshape(B, L, heads, d).permute(0, 2, 1, 3) for t in qkv.split(C, dim=-1))
+    errs = []
+    for b0 in range(0, B, 8):          # reference on the GPU in fp64, a few samples at a time (B*h*L*L scores)
+        sl = slice(b0, min(B, b0 + 8))
+        ref = (torch.softmax(q[sl] @ k[sl].transpose(-1, -2) / math.sqrt(d), -1) @ v[sl]).permute(0, 2, 1, 3).reshape(-1, L, C)
+        errs.append(G.rel_l2(o[sl].double(), ref))
+    assert max(errs) < 3e-3, errs
+
+
 ATTN_BLOCK_CASES = [(64, 64, 128, 4), (64, 16, 256, 4), (64, 4, 512, 4), (5, 4, 512, 4), (3, 16, 256, 4), (3, 64, 128, 4),
                     (7, 1, 512, 4), (4, 16, 256, 8), (2, 64, 256, 8), (9, 2, 128, 4), (3, 32, 512, 8)]
 
