@@ -47,6 +47,8 @@ WORKLOADS = {
     "cfg4": dict(case="cfg4_downscale_64", global_batch=64, scaling="weak", flops=17.75e9),   # 64 per GPU = 512 on 8 GPUs
     "cfg5": dict(case="cfg5_flexible_128", global_batch=256, scaling="strong", flops=12.527e9),
 }
+# BASELINE configs[4]: 1024-member ensemble through the native generation driver (b2d_ensemble_run): dates x members per date
+ENSEMBLE = dict(case="cfg5_flexible_128", dates=16, members=64, sub_batch=128, flops=12.527e9)
 # reference arm / cpu_baseline: (sub-batch, reverse steps per timed call) sized for ~1-2 s per call on 16 host cores
 REF_SAMPLE = {"cfg1": (4, 8), "cfg2": (8, 4), "cfg3": (4, 2), "cfg4": (4, 2), "cfg5": (4, 2)}
 HEAD_DIM_OF_CLASS = {"attn_tc": 16, "attn_tc32": 32}
@@ -276,6 +278,44 @@ class Bench:
         return res
 
 
+def run_ensemble(B: "Bench"):
+    """cfg5: 16 dates x 64 members = 1024 fields of the modules_DANRA_flexible network at 128x128 through generate_ensemble
+    (host conditioning per date -> native sub-batch scheduler -> host fields); members sharded over the ranks."""
+    import torch.distributed as dist
+    from diffusionmodelscustom_b200 import DiffusionUtils, generate_ensemble, synth
+    from diffusionmodelscustom_b200.configs import R_CASES, build_ours_r
+    case = R_CASES[ENSEMBLE["case"]]
+    net, _ = build_ours_r(case, B.dev)
+    D, M, sb = ENSEMBLE["dates"], ENSEMBLE["members"], ENSEMBLE["sub_batch"]
+    inp = synth.synth_inputs(D, case["hw"], seed=case["iseed"], has_lsm=True, has_topo=True, has_cond=True, num_classes=4)
+    du = DiffusionUtils(T_STEPS, 1e-4, 0.02, B.dev, "linear")
+    kw = dict(season=inp["y"], cond_img=inp["cond"], lsm=inp["lsm"], topo=inp["topo"], sub_batch=sb, device=B.dev, gather=False,
+              return_stats=True)
+    per_rank = D * M // B.world
+    warm_members = max(1, min(sb, per_rank) * B.world // D)        # one sub-batch per rank: builds the program and the graphs
+    generate_ensemble(net, du, D, warm_members, seed=1, **kw)
+    B.barrier()
+    t0 = time.perf_counter()
+    out, st = generate_ensemble(net, du, D, M, seed=2, **kw)
+    B.barrier()
+    wall = time.perf_counter() - t0
+    if B.world > 1:
+        t = torch.tensor([wall], device=B.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    assert torch.isfinite(out).all()
+    total = D * M
+    del net
+    torch.cuda.empty_cache()
+    return {"name": "cfg5", "workload": (f"cfg5: Family R DiffusionNet (modules_DANRA_flexible), 128x128, full conditioning, {total}-member "
+                                          f"ensemble = {D} dates x {M} members through generate_ensemble / b2d_ensemble_run, T={T_STEPS}"),
+            "value": total / wall, "unit": "samples/s", "end_to_end": True, "wall_s": wall, "members": total,
+            "sub_batch": sb, "sub_batches_per_rank": st["sub_batches"], "out_pinned": st["out_pinned"],
+            "host_gather_ms": st["gather_ms"], "gpu_launches": st["launches"],
+            "tflops_per_gpu": total / wall * ENSEMBLE["flops"] * (T_STEPS - 1) / 1e12 / B.world,
+            "note": "host conditioning per date in, host fields out; timed by wall clock between barriers, max over ranks"}
+
+
 def class_rooflines(prof, pk):
     """Per kernel class of one reverse step: share, launches, achieved TFLOP/s / GB/s / Texp/s against the burst peaks."""
     by = {}
@@ -315,7 +355,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=list(WORKLOADS))
     ap.add_argument("--global-batch", type=int, default=0, help="override the workload's global batch")
-    ap.add_argument("--secondary", default="cfg2,cfg4", help="comma list of workloads carried as secondary objects ('' = none)")
+    ap.add_argument("--secondary", default="cfg2,cfg4,cfg5", help="comma list of workloads carried as secondary objects ('' = none); "
+                    "cfg5 = the 1024-member ensemble through the generation driver")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed host end-to-end steps (default min(steps, 3))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -344,6 +385,11 @@ def main():
     clocks = sampler.stop() if sampler else None
     secondary = {}
     for name in [s for s in args.secondary.split(",") if s and s != args.workload]:
+        if name == "cfg5":
+            r = run_ensemble(B)
+            if rank == 0:
+                secondary[name] = r
+            continue
         r = B.run_workload(name, min(args.steps, 2), 1, 1, None, profile=True)
         if rank == 0:
             pk = peaks()

@@ -9,8 +9,10 @@ from .modules import Decoder, DecoderBlock, DiffusionNet, Encoder, ImageSelfAtte
 from .diffusion import Diffusion, DiffusionUtils, DiffusionUtilsV2  # noqa: F401
 from .unet_ms import UNet_downscale  # noqa: F401
 from .generation import generate_ensemble, load_checkpoint, save_bundle  # noqa: F401
+from . import evaluation  # noqa: F401
+from .evaluation import SDFWeightedMSELoss  # noqa: F401
 from . import unet  # noqa: F401  (DDPM_clean_application/src/unet.py generation: unet.Encoder / unet.Decoder / unet.DiffusionNet)
 
 __all__ = ["Encoder", "Decoder", "DecoderBlock", "DiffusionNet", "ImageSelfAttention", "SinusoidalEmbedding", "UNet",
            "DiffusionUtils", "DiffusionUtilsV2", "Diffusion", "UNet_downscale", "generate_ensemble", "load_checkpoint",
-           "save_bundle"]
+           "save_bundle", "SDFWeightedMSELoss", "evaluation"]

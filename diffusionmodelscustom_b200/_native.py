@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2D_LIB") or os.path.join(_PKG, "libb200ddpm.so")   # B2D_LIB: an instrumented build (tools/attn_trace.py)
 
 FAMILY_R, FAMILY_D = 0, 1
+INTERP_MODES = {"bicubic": 0, "bilinear": 1, "nearest": 2}
 
 # every symbol include/b200ddpm.h declares (tests check that the library exports all of them)
 SYMBOLS = ["b2d_last_error", "b2d_abi_version", "b2d_create", "b2d_destroy", "b2d_load_weights", "b2d_set_schedule",
@@ -22,7 +23,8 @@ SYMBOLS = ["b2d_last_error", "b2d_abi_version", "b2d_create", "b2d_destroy", "b2
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("family", "img_size", "max_batch", "c_hr", "c_out", "has_lsm", "has_topo",
-                                         "cond_channels", "num_classes", "n_heads", "attn_ff", "debug_simt_conv")]
+                                         "cond_channels", "num_classes", "n_heads", "attn_ff", "debug_simt_conv",
+                                         "interp_mode", "stem_embedding")]
 
 
 class Tensor(C.Structure):

@@ -29,6 +29,11 @@ R_CASES = {
     "full_64_bigx": _r(64, 2, True, True, True, 4, ts=(40,), x_scale=300.0, wseed=44, iseed=9),
     # smallest legal field (fmap5 is 1x1, attention over a single token), other head count
     "full_32_heads8": _r(32, 2, True, True, True, 4, ts=(321,), n_heads=8, wseed=45, iseed=10),
+    # Downscaling generation (DDPM_DANRA_Downscaling): unconditional, encoder embeds t with the interleaved base-10000 embedding
+    "downscaling_uncond_64": _r(64, 2, False, False, False, None, ts=(999, 321, 1), wseed=48, iseed=13, downscaling=True,
+                                module="modules_DANRA_downscaling"),
+    # launcher default of the clean application (test/launch.py:62): ONE attention head (head_dim = C = 64 ... 512)
+    "cfg2_heads1_64": _r(64, 2, True, True, False, None, ts=(700,), n_heads=1, wseed=49, iseed=14),
     # newest generation (DDPM_clean_application/src/unet.py): attention with FF tail, cond_on_lsm/topo flags, 8 heads
     "clean_ff_64_heads8": _r(64, 2, True, True, True, 4, ts=(999, 77), n_heads=8, wseed=47, iseed=12, clean=True),
 }
@@ -37,6 +42,9 @@ D_CASES = {
     # cfg 4: UNet_downscale 64x64, HR + bicubic-upsampled low-res field, c_in = 2
     "cfg4_downscale_64": dict(hw=64, batch=2, c_in=2, lowres=8, ts=[999, 300, 1], wseed=42, iseed=7),
     "downscale_32": dict(hw=32, batch=3, c_in=2, lowres=4, ts=[555], wseed=46, iseed=11),
+    # the other F.interpolate modes of UNet_downscale(interp_mode=...) (unet_ms.py:105,156); non-integer scale factor 32/5
+    "downscale_32_bilinear": dict(hw=32, batch=2, c_in=2, lowres=5, ts=[400], wseed=46, iseed=15, interp_mode="bilinear"),
+    "downscale_32_nearest": dict(hw=32, batch=2, c_in=2, lowres=5, ts=[400], wseed=46, iseed=16, interp_mode="nearest"),
 }
 
 SAMPLE_CASES = {
@@ -73,6 +81,13 @@ def build_ours_r(case, device="cuda"):
         net.load_state_dict(sd, strict=True)
         net.eval()
         return net.to(device), sd
+    if case.get("downscaling"):
+        from . import downscaling as DS
+        net = DS.DiffusionNet(DS.Encoder(1, 256, n_heads=case.get("n_heads", 4)), DS.Decoder(512, 1, 256, 64, n_heads=case.get("n_heads", 4)))
+        sd = synth.synth_state_dict_r(1, 1, None, (H, H), False, False, seed=case["wseed"], randomize_bn=case["randomize_bn"])
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        return net.to(device), sd
     z = torch.zeros(1, H, H)
     enc = _pkg().Encoder(1, 256, lsm_tensor=z if case["has_lsm"] else None, topo_tensor=z.clone() if case["has_topo"] else None,
                     cond_on_img=case["has_cond"], cond_img_dim=(1, H, H) if case["has_cond"] else None,
@@ -95,7 +110,8 @@ def inputs_r(case, batch=None, device="cuda"):
 
 
 def build_ours_d(case, device="cuda"):
-    net = _pkg().UNet_downscale(c_in=case["c_in"], c_out=1, time_dim=256, interp_mode="bicubic", img_size=case["hw"], device=device)
+    net = _pkg().UNet_downscale(c_in=case["c_in"], c_out=1, time_dim=256, interp_mode=case.get("interp_mode", "bicubic"),
+                                img_size=case["hw"], device=device)
     sd = synth.synth_state_dict_d(case["c_in"], 1, seed=case["wseed"])
     net.load_state_dict(sd, strict=True)
     net.eval()

@@ -300,7 +300,79 @@ __global__ void __launch_bounds__(128) attn_small_d_kernel(const f16* __restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------ wide heads, few tokens
+// head_dim 256 / 512 only occurs with n_heads = 1 (the launcher default of the clean application, test/launch.py:62) at the
+// low-resolution levels (C = 256: L = 16 / 64 tokens, C = 512: L = 4 / 16): a few MFLOP per sample.  One CTA per (sample, head):
+// Q, K, V of the head in shared memory, the L x L scores in fp32, softmax per row, O = P V.  Requires L <= 64, L * D <= 16384.
+constexpr int AW_MAX_L = 64;
+constexpr int AW_MAX_LD = 16384;
+__global__ void __launch_bounds__(256) attn_wide_kernel(const f16* __restrict__ qkv, f16* __restrict__ o, int L, int C, int D,
+                                                        float scale) {
+    pdl_launch_dependents();
+    extern __shared__ uint8_t aw_raw[];
+    f16* sq = reinterpret_cast<f16*>(aw_raw);                 // [L][D]
+    f16* sk = sq + (size_t)L * D;
+    f16* sv = sk + (size_t)L * D;
+    float* sp = reinterpret_cast<float*>(sv + (size_t)L * D);  // [L][L]
+    const int head = blockIdx.x, b = blockIdx.y;
+    pdl_wait();
+    const f16* base = qkv + (size_t)b * L * 3 * C + (size_t)head * D;
+    const int d8 = D >> 3;
+    for (int i = threadIdx.x; i < L * d8; i += blockDim.x) {
+        const int r = i / d8, c8 = (i - r * d8) * 8;
+        const f16* row = base + (size_t)r * 3 * C + c8;
+        *reinterpret_cast<uint4*>(sq + (size_t)r * D + c8) = __ldg(reinterpret_cast<const uint4*>(row));
+        *reinterpret_cast<uint4*>(sk + (size_t)r * D + c8) = __ldg(reinterpret_cast<const uint4*>(row + C));
+        *reinterpret_cast<uint4*>(sv + (size_t)r * D + c8) = __ldg(reinterpret_cast<const uint4*>(row + 2 * C));
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int ij = warp; ij < L * L; ij += nw) {               // one warp per score: lanes stride the head dimension
+        const int i = ij / L, j = ij - i * L;
+        float acc = 0.f;
+        for (int c = lane * 2; c < D; c += 64) {
+            const float2 a = __half22float2(*reinterpret_cast<const f162*>(sq + (size_t)i * D + c));
+            const float2 k2 = __half22float2(*reinterpret_cast<const f162*>(sk + (size_t)j * D + c));
+            acc = fmaf(a.x, k2.x, acc);
+            acc = fmaf(a.y, k2.y, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sp[ij] = acc * scale;
+    }
+    __syncthreads();
+    for (int i = warp; i < L; i += nw) {                       // softmax of row i
+        float m = -INFINITY;
+        for (int j = lane; j < L; j += 32) m = fmaxf(m, sp[i * L + j]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        float sum = 0.f;
+        for (int j = lane; j < L; j += 32) {
+            const float e = __expf(sp[i * L + j] - m);
+            sp[i * L + j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < L; j += 32) sp[i * L + j] *= inv;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < L * (D >> 1); idx += blockDim.x) {   // O[i][c..c+1] = sum_j P[i][j] V[j][c..c+1]
+        const int i = idx / (D >> 1), c = (idx - i * (D >> 1)) * 2;
+        float a0 = 0.f, a1 = 0.f;
+        for (int j = 0; j < L; ++j) {
+            const float pj = sp[i * L + j];
+            const float2 v2 = __half22float2(*reinterpret_cast<const f162*>(sv + (size_t)j * D + c));
+            a0 = fmaf(pj, v2.x, a0);
+            a1 = fmaf(pj, v2.y, a1);
+        }
+        *reinterpret_cast<uint32_t*>(o + ((size_t)b * L + i) * C + (size_t)head * D + c) = pack_h2(a0, a1);
+    }
+}
+inline bool attn_wide_supported(int L, int D) { return (D == 256 || D == 512) && L <= AW_MAX_L && L * D <= AW_MAX_LD; }
+
 inline int flash_attn_init_attrs() {
+    B2D_CUDA(cudaFuncSetAttribute(attn_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  3 * AW_MAX_LD * 2 + AW_MAX_L * AW_MAX_L * 4));
     B2D_CUDA(cudaFuncSetAttribute(flash_attn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   fa_smem_bytes<128>()));
     B2D_CUDA(cudaFuncSetAttribute(flash_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -321,7 +393,12 @@ inline int flash_attn_launch(const f16* qkv, f16* o, int B, int L, int C, int he
         case 32: B2D_CUDA(launch_k(flash_attn_kernel<32>, dim3(grid), dim3(128), fa_smem_bytes<32>(), st, qkv, o, L, C, scale_log2e)); break;
         case 64: B2D_CUDA(launch_k(flash_attn_kernel<64>, dim3(grid), dim3(128), fa_smem_bytes<64>(), st, qkv, o, L, C, scale_log2e)); break;
         case 128: B2D_CUDA(launch_k(flash_attn_kernel<128>, dim3(grid), dim3(128), fa_smem_bytes<128>(), st, qkv, o, L, C, scale_log2e)); break;
-        default: return fail(-1, "attention: unsupported head_dim " + std::to_string(D));
+        default:
+            if (!attn_wide_supported(L, D))
+                return fail(-1, "attention: unsupported head_dim " + std::to_string(D) + " at " + std::to_string(L) + " tokens");
+            B2D_CUDA(launch_k(attn_wide_kernel, dim3(heads, B), dim3(256), (size_t)3 * L * D * 2 + (size_t)L * L * 4, st, qkv, o, L, C, D,
+                              1.0f / sqrtf((float)D)));
+            break;
     }
     B2D_CUDA(cudaGetLastError());
     return 0;

@@ -676,7 +676,7 @@ static int build_program_r(Handle* h, int B) {
         ops.push_back([=](cudaStream_t st) {
             dim3 grid((TS + TEMB_OC - 1) / TEMB_OC, (B + TEMB_SB - 1) / TEMB_SB);
             B2D_CUDA(launch_k(temb_project_kernel, dim3(grid), dim3(256), 0, st, hh->d_t, hh->has_y ? hh->d_y : nullptr, label, ei, dd, tw, tb, temb, 1024,
-                                                      TS, B, hh->temb_t_off));
+                                                      TS, B, hh->temb_t_off, hh->cfg.stem_embedding));
             B2D_CUDA(cudaGetLastError());
             return 0;
         });
@@ -846,6 +846,7 @@ static int init_uniform_carveout() {
     B2D_TRY(set_carveout(posterior_update_kernel));
     B2D_TRY(set_carveout(fill_int_kernel));
     B2D_TRY(set_carveout(bicubic_resize_kernel));
+    B2D_TRY(set_carveout(linear_nearest_resize_kernel));
     B2D_TRY(set_carveout(sample_stats_kernel));
     B2D_TRY(set_carveout(groupnorm_apply_kernel));
     B2D_TRY(set_carveout(maxpool2_kernel));
@@ -1445,7 +1446,8 @@ int b2d_op_attn_block_out(const void* x, const void* w_folded, const float* c1, 
     B2D_TRY(attn_block_plan_build(pl, (const f16*)x, (const f16*)w_folded, c1, bias, nullptr, B * L, C, L, heads));
     float* ws = nullptr;
     B2D_CUDA(cudaMalloc(&ws, attn_block_ws_floats(B * L, C, heads) * sizeof(float)));
-    const bool gather = getenv("B2D_NO_ATTN_GATHER") == nullptr && attn_block_gather_supported(C, heads);
+    // same polarity as the model program: the DSMEM-gather variant is opt-in (measured slower; B2D_ATTN_GATHER=1 selects it)
+    const bool gather = getenv("B2D_ATTN_GATHER") != nullptr && attn_block_gather_supported(C, heads);
     int rc = attn_block_plan_fuse_out(pl, (const f16*)wo, out_bias, (const f16*)x, (f16*)y, ws, final_act, gather ? 2 : 1);
     if (rc == 0) rc = attn_block_launch(pl, as_stream(stream));
     cudaStreamSynchronize(as_stream(stream));

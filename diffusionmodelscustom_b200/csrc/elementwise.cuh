@@ -22,13 +22,15 @@ __global__ void __launch_bounds__(256) temb_project_kernel(const int* __restrict
                                                            const float* __restrict__ W,          // [n_out][256]
                                                            const float* __restrict__ bias,       // [n_out]
                                                            float* __restrict__ out,              // [B][n_out]
-                                                           int n_enc, int n_out, int B, int t_off) {
+                                                           int n_enc, int n_out, int B, int t_off, int enc_interleaved) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float se[TEMB_SB][TEMB_DIM];   // silu(embedding) of this CTA's samples (encoder OR decoder flavour)
     const int b0 = blockIdx.y * TEMB_SB;
     const int o0 = blockIdx.x * TEMB_OC;
-    const bool enc = o0 < n_enc;              // n_enc is a multiple of TEMB_OC (host-checked): a CTA is all-encoder or all-decoder
+    // n_enc is a multiple of TEMB_OC (host-checked): a CTA is all-encoder or all-decoder.  enc_interleaved: the Downscaling
+    // generation's encoder embeds t with the decoder's interleaved base-10000 SinusoidalEmbedding (modules_DANRA_downscaling.py:190)
+    const bool enc = o0 < n_enc && !enc_interleaved;
     {
         const int k = threadIdx.x;  // 256 threads <-> 256 embedding entries
         // inside the reverse loop every sample carries the same t: the sin/cos is evaluated once and reused

@@ -139,11 +139,13 @@ __global__ void __launch_bounds__(256) histogram_kernel(const float* __restrict_
     extern __shared__ unsigned int sh_bins[];
     for (int i = threadIdx.x; i < bins; i += blockDim.x) sh_bins[i] = 0;
     __syncthreads();
-    const float scale = (float)bins / (hi - lo);
+    // bin index in double, like numpy ((x - first_edge) * bins / (last_edge - first_edge) on float64): with thousands of bins an
+    // fp32 product misplaces every value within ~1e-4 of an edge
+    const double scale = (double)bins / ((double)hi - (double)lo);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float v = x[i];
         if (v >= lo && v <= hi) {                       // NaN fails both comparisons
-            int b = (int)((v - lo) * scale);
+            int b = (int)(((double)v - (double)lo) * scale);
             if (b >= bins) b = bins - 1;                // right edge belongs to the last bin
             atomicAdd(&sh_bins[b], 1u);
         }

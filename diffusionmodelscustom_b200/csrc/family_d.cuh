@@ -47,6 +47,34 @@ __global__ void __launch_bounds__(256) bicubic_resize_kernel(const float* __rest
     }
 }
 
+// F.interpolate(y, size, mode='bilinear') (align_corners=False: src = scale * (dst + 0.5) - 0.5 clamped at 0) and
+// mode='nearest' (src = floor(dst * scale)): the other interp_mode values of UNet_downscale (unet_ms.py:105,156).
+__global__ void __launch_bounds__(256) linear_nearest_resize_kernel(const float* __restrict__ in, float* __restrict__ out, int planes,
+                                                                    int hi, int wi, int Ho, int Wo, int nearest) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t total = (size_t)planes * Ho * Wo;
+    const float sh = (float)hi / (float)Ho, sw = (float)wi / (float)Wo;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int ox = (int)(idx % Wo);
+        const int oy = (int)((idx / Wo) % Ho);
+        const float* p = in + (size_t)(idx / ((size_t)Wo * Ho)) * hi * wi;
+        if (nearest) {
+            const int iy = min((int)floorf(oy * sh), hi - 1), ix = min((int)floorf(ox * sw), wi - 1);
+            out[idx] = p[(size_t)iy * wi + ix];
+            continue;
+        }
+        const float ry = fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f), rx = fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
+        const int y0 = (int)ry, x0 = (int)rx;
+        const int y1 = y0 + (y0 < hi - 1 ? 1 : 0), x1 = x0 + (x0 < wi - 1 ? 1 : 0);
+        const float ly = ry - (float)y0, lx = rx - (float)x0;
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        // torch's upsample_bilinear2d order: h0 * (w0 * a + w1 * b) + h1 * (w0 * c + w1 * d)
+        out[idx] = hy * (hx * p[(size_t)y0 * wi + x0] + lx * p[(size_t)y0 * wi + x1]) +
+                   ly * (hx * p[(size_t)y1 * wi + x0] + lx * p[(size_t)y1 * wi + x1]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ GroupNorm(1, C)
 // Per-sample {mean, rstd} over all C*H*W elements of an NHWC f16 tensor (biased variance, eps 1e-5).  Deterministic:
 // per-slab partials, last-arriving CTA of a sample adds them in slab order.  grid = (nslab, B).
@@ -491,7 +519,7 @@ static int build_program_d(Handle* h, int B) {
         ops.meta("temb", "temb_project", 2.0 * B * TS * 256, 4.0 * TS * 256);
         ops.push_back([=](cudaStream_t st) {
             dim3 grid((TS + TEMB_OC - 1) / TEMB_OC, (B + TEMB_SB - 1) / TEMB_SB);
-            B2D_CUDA(launch_k(temb_project_kernel, grid, dim3(256), 0, st, hh->d_t, nullptr, nullptr, ei, dd, tw, tb, temb, TS, TS, B, hh->temb_t_off));
+            B2D_CUDA(launch_k(temb_project_kernel, grid, dim3(256), 0, st, hh->d_t, nullptr, nullptr, ei, dd, tw, tb, temb, TS, TS, B, hh->temb_t_off, 0));
             return 0;
         });
     }
@@ -598,7 +626,11 @@ static int set_conditioning_d(Handle* h, const float* cond, int ch, int cw, int 
     const int planes = B * c.cond_channels;
     const size_t total = (size_t)planes * H * H;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
-    B2D_CUDA(launch_k(bicubic_resize_kernel, dim3(blocks), dim3(256), 0, st, cond, h->d_cond_stack, planes, ch, cw, H, H));
+    if (c.interp_mode == B2D_INTERP_BICUBIC)
+        B2D_CUDA(launch_k(bicubic_resize_kernel, dim3(blocks), dim3(256), 0, st, cond, h->d_cond_stack, planes, ch, cw, H, H));
+    else
+        B2D_CUDA(launch_k(linear_nearest_resize_kernel, dim3(blocks), dim3(256), 0, st, cond, h->d_cond_stack, planes, ch, cw, H, H,
+                          c.interp_mode == B2D_INTERP_NEAREST ? 1 : 0));
     dim3 grid(H / 16, H / 16, B);
     B2D_CUDA(launch_k(stem_conv_kernel<3, 1>, grid, dim3(256), 0, st, (const float*)h->d_cond_stack, c.cond_channels, H, H,
                       (const float*)h->dev["inc.stem.w"], c.c_hr + c.cond_channels, c.c_hr, (const float*)nullptr,

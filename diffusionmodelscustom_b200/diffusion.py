@@ -48,12 +48,31 @@ class DiffusionUtils:
     def sampleTimesteps(self, size: int):
         return torch.randint(low=1, high=self.n_timesteps, size=(size,)).to(self.device)
 
-    def noiseImage(self, x: torch.Tensor, t: torch.LongTensor):
-        """Forward process q(x_t | x_0) (diffusion_DANRA_conditional.py:85-103); training-side, plain torch."""
+    def noiseImage(self, x: torch.Tensor, t: torch.LongTensor, *, noise: torch.Tensor = None, seed: int = None):
+        """Forward process q(x_t | x_0) (diffusion_DANRA_conditional.py:85-103): returns (x_t, noise).
+
+        CUDA tensors go through ONE fused kernel (``b2d_op_noise_image``): the gather of alpha_hat[t], both square roots, the
+        normal draw (Philox, keyed by ``seed`` — taken from torch's global generator when omitted — or the injected ``noise``),
+        the data_scaled factor and the blend, writing x_t and the noise in the same pass.  CPU tensors follow the reference's
+        torch expressions (training-side convenience, not on the sampling path)."""
         assert len(x.shape) == 4, 'x must be a 4D tensor'
+        scale = 0.005 if self.data_scaled else 1.0
+        if x.is_cuda:
+            xx = x.detach().to(torch.float32).contiguous()
+            tt = t.detach().to(x.device, torch.int64).contiguous()
+            ah = self.alpha_hat.detach().to(x.device, torch.float32).contiguous()
+            nz = None if noise is None else noise.detach().to(x.device, torch.float32).contiguous()
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            x_t, eps = torch.empty_like(xx), torch.empty_like(xx)
+            with torch.cuda.device(x.device):
+                N.check(N.lib().b2d_op_noise_image(xx.data_ptr(), tt.data_ptr(), ah.data_ptr(), N.ptr(nz), x_t.data_ptr(),
+                                                   eps.data_ptr(), xx.shape[0], xx[0].numel(), int(seed), 0, float(scale),
+                                                   torch.cuda.current_stream().cuda_stream))
+            return x_t, eps
         alpha_hat_sqrts = torch.sqrt(self.alpha_hat[t])[:, None, None, None]
         one_minus_alpha_hat_sqrt = torch.sqrt(1 - self.alpha_hat[t])[:, None, None, None]
-        noise = torch.randn_like(x).to(self.device)
+        noise = torch.randn_like(x).to(self.device) if noise is None else noise.clone()
         if self.data_scaled:
             noise *= 0.005
         return (alpha_hat_sqrts * x) + (one_minus_alpha_hat_sqrt * noise), noise

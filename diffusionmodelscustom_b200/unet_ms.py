@@ -60,8 +60,8 @@ class UNet_downscale(NativeModel):
         super().__init__()
         if time_dim != 256:
             raise NotImplementedError("time_dim must be 256")
-        if interp_mode != 'bicubic':
-            raise NotImplementedError("only interp_mode='bicubic' (the reference default) is built natively")
+        if interp_mode not in N.INTERP_MODES:
+            raise NotImplementedError(f"interp_mode must be one of {sorted(N.INTERP_MODES)} (F.interpolate modes built natively)")
         self.device = device
         self.time_dim = time_dim
         self.interp_mode = interp_mode
@@ -90,7 +90,7 @@ class UNet_downscale(NativeModel):
                              "(unet_ms.py:121-135)")
         return N.Config(family=N.FAMILY_D, img_size=img_size, max_batch=max_batch, c_hr=self._c_hr, c_out=self.c_out,
                         has_lsm=0, has_topo=0, cond_channels=self.c_in - self._c_hr, num_classes=0, n_heads=4, attn_ff=1,
-                        debug_simt_conv=int(self.debug_simt_conv))
+                        debug_simt_conv=int(self.debug_simt_conv), interp_mode=N.INTERP_MODES[self.interp_mode])
 
     def _set_conditioning(self, h, B, y, cond_img, lsm_cond, topo_cond, stream):
         low = cond_img if cond_img is not None else y     # the low-res field is forward()'s third positional argument

@@ -48,7 +48,12 @@ typedef struct b2d_config {
     int32_t n_heads;       /* attention heads (default 4) */
     int32_t attn_ff;       /* 1: attention block has the LN-Linear-GELU-Linear tail (src/unet.py:91-96, unet_ms.py:13-18) */
     int32_t debug_simt_conv; /* 1: run GEMM-shaped ops on the CUDA-core cross-check kernel (bring-up only) */
+    int32_t interp_mode;   /* Family D: F.interpolate mode of the low-resolution field (unet_ms.py:105,156): B2D_INTERP_* */
+    int32_t stem_embedding; /* Family R: 0 = Encoder.pos_encoding (base 1000, [sin | cos] halves, modules_DANRA_conditional.py:203-211);
+                              1 = the interleaved base-10000 SinusoidalEmbedding the Downscaling generation uses in its encoder
+                              (DDPM_DANRA_Downscaling/modules_DANRA_downscaling.py:190-197) */
 } b2d_config;
+enum { B2D_INTERP_BICUBIC = 0, B2D_INTERP_BILINEAR = 1, B2D_INTERP_NEAREST = 2 };
 
 /* One named FP32 tensor of a reference state_dict (host memory, contiguous, torch layout). */
 typedef struct b2d_tensor {

@@ -121,7 +121,7 @@ def _tproj(sd, p, temb):
 
 # --------------------------------------------------------------------------- Family R
 def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=None, n_heads=4,
-                     has_lsm=None, has_topo=None, taps=None):
+                     has_lsm=None, has_topo=None, taps=None, downscaling=False):
     """DiffusionNet.forward (modules_DANRA_conditional.py:597-616) = Decoder(*Encoder(...), t).
 
     has_lsm/has_topo mirror ``hasattr(self,'lsm')`` / ``hasattr(self,'elevation')`` (:228-233) and
@@ -143,7 +143,8 @@ def family_r_forward(sd, x, t, y=None, cond_img=None, lsm_cond=None, topo_cond=N
         x = torch.cat([x, topo_cond], dim=1)
     if cond_img is not None:
         x = torch.cat((x, cond_img), dim=1)
-    temb = enc_time_embedding(t)                                    # :243-244
+    # :243-244; the Downscaling generation embeds t with SinusoidalEmbedding instead (modules_DANRA_downscaling.py:190)
+    temb = dec_time_embedding(t) if downscaling else enc_time_embedding(t)
     if y is not None:
         temb = temb + sd[E + "label_emb.weight"][y]                 # :256
     fm = []

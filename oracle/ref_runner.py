@@ -60,6 +60,10 @@ def build_ref_r(case, synth, module_name="modules_DANRA_conditional"):
         net = mod.DiffusionNet(enc, dec)
         sd = synth.synth_state_dict_r(case["c_in"], 1, case["num_classes"], (H, H), case["has_lsm"], case["has_topo"],
                                       seed=case["wseed"], randomize_bn=case["randomize_bn"], clean=True)
+    elif case.get("downscaling"):
+        mod = import_ref("modules_DANRA_downscaling")
+        net = mod.DiffusionNet(mod.Encoder(1, 256, n_heads=case.get("n_heads", 4)), mod.Decoder(512, 1, 256, 64, n_heads=case.get("n_heads", 4)))
+        sd = synth.synth_state_dict_r(1, 1, None, (H, H), False, False, seed=case["wseed"], randomize_bn=case["randomize_bn"])
     else:
         mod = import_ref(case.get("module", module_name))
         lsm = torch.zeros(1, H, H) if case["has_lsm"] else None

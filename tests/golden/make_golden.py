@@ -40,7 +40,10 @@ def run_r(case):
         for t in case["ts"]:
             tt = torch.full((case["batch"],), t, dtype=torch.long)
             x = inp["x"] * case.get("x_scale", 1.0)
-            out[f"eps_t{t}"] = net(x, tt, inp["y"], inp["cond"], inp["lsm"], inp["topo"]).numpy()
+            if case.get("downscaling"):
+                out[f"eps_t{t}"] = net(x, tt).numpy()
+            else:
+                out[f"eps_t{t}"] = net(x, tt, inp["y"], inp["cond"], inp["lsm"], inp["topo"]).numpy()
     return out
 
 

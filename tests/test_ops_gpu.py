@@ -122,7 +122,9 @@ def test_layernorm(C):
 
 
 ATTN_CASES = [(2, 1024, 64, 4), (2, 256, 64, 4), (3, 64, 128, 4), (3, 16, 256, 4), (5, 4, 512, 4), (2, 1, 512, 4),
-              (2, 100, 64, 4), (2, 256, 64, 8), (1, 64, 128, 32), (2, 4096, 64, 4), (2, 16, 128, 1)]
+              (2, 100, 64, 4), (2, 256, 64, 8), (1, 64, 128, 32), (2, 4096, 64, 4), (2, 16, 128, 1),
+              # n_heads = 1 (launcher default of the clean application): head_dim = C up to 512
+              (3, 16, 256, 1), (3, 64, 256, 1), (5, 4, 512, 1), (2, 16, 512, 1), (2, 1024, 64, 1), (2, 256, 64, 1)]
 
 
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}" for b, l, c, h in ATTN_CASES])

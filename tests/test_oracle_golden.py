@@ -37,7 +37,7 @@ def test_family_r_eps_matches_reference(name, golden_dir):
         tt = torch.full((case["batch"],), t, dtype=torch.long)
         with torch.no_grad():
             eps = O.family_r_forward(sd, inp["x"] * case.get("x_scale", 1.0), tt, inp["y"], inp["cond"], inp["lsm"],
-                                     inp["topo"], n_heads=case.get("n_heads", 4))
+                                     inp["topo"], n_heads=case.get("n_heads", 4), downscaling=case.get("downscaling", False))
         assert rel_l2(eps, gold[f"eps_t{t}"]) < TOL, (name, t)
 
 
@@ -50,7 +50,7 @@ def test_family_d_eps_matches_reference(name, golden_dir):
     for t in case["ts"]:
         tt = torch.full((case["batch"],), t, dtype=torch.long)
         with torch.no_grad():
-            eps = O.family_d_forward(sd, inp["x"], tt, inp["y_lowres"])
+            eps = O.family_d_forward(sd, inp["x"], tt, inp["y_lowres"], interp_mode=case.get("interp_mode", "bicubic"))
         assert rel_l2(eps, gold[f"eps_t{t}"]) < TOL, (name, t)
 
 
