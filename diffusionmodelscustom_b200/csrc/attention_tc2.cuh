@@ -80,12 +80,12 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t addr, uint32_t parity) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "WAIT_LOOP_A:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE_A;\n\t"
-        "bra WAIT_LOOP_A;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"   // %2: suspend-time hint — the thread sleeps in the
+        "@P1 bra DONE_A;\n\t"                                               // barrier unit instead of re-issuing try_wait + branch
+        "bra WAIT_LOOP_A;\n\t"                                              // (a fifth of all issued instructions without it)
         "DONE_A:\n\t"
         "}" ::"r"(addr),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit_a(uint32_t addr) {

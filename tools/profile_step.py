@@ -1,6 +1,6 @@
 """Profiling driver: N plain eps evaluations of a bench workload (one reverse step each, ~85 launches), so that ncu can
 capture exactly one step (`-s <launches> -c <launches>`), plus the live per-launch CUDA-event table (b2d_profile_step).
-    python tools_profile_step.py [--workload cfg2] [--batch 64] [--iters 3] [--perop gpurun_out/perop.json]"""
+    python tools/profile_step.py [--workload cfg2] [--batch 64] [--iters 3] [--perop gpurun_out/perop.json]"""
 import argparse
 import json
 import sys
@@ -18,8 +18,8 @@ ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--perop", default="")
 ap.add_argument("--sample-steps", type=int, default=0, help="also run a short reverse loop (posterior update kernel)")
 a = ap.parse_args()
-case_name, batch, _ = WORKLOADS[a.workload]
-batch = a.batch or batch
+case_name = WORKLOADS[a.workload]["case"]
+batch = a.batch or WORKLOADS[a.workload]["global_batch"]
 if case_name in D_CASES:
     case = D_CASES[case_name]
     net, _ = build_ours_d(case)
