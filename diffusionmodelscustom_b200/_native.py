@@ -18,7 +18,7 @@ INTERP_MODES = {"bicubic": 0, "bilinear": 1, "nearest": 2}
 SYMBOLS = ["b2d_last_error", "b2d_abi_version", "b2d_create", "b2d_destroy", "b2d_load_weights", "b2d_set_schedule",
            "b2d_set_conditioning", "b2d_forward", "b2d_sample", "b2d_sample_host", "b2d_last_launch_count", "b2d_debug_read", "b2d_profile_step",
            "b2d_op_conv2d", "b2d_op_layernorm", "b2d_op_attention", "b2d_op_attn_block", "b2d_op_attn_block_out", "b2d_op_instnorm", "b2d_op_posterior_update", "b2d_saturation_count", "b2d_debug_attn_trace", "b2d_ensemble_run",
-           "b2d_op_noise_image", "b2d_op_weighted_mse", "b2d_op_eval_daily", "b2d_op_eval_pixel", "b2d_op_histogram"]
+           "b2d_op_noise_image", "b2d_op_weighted_mse", "b2d_op_eval_daily", "b2d_op_eval_pixel", "b2d_op_histogram", "b2d_encoder_forward", "b2d_decoder_forward"]
 
 
 class Config(C.Structure):
@@ -83,6 +83,8 @@ def lib():
         L.b2d_op_eval_daily.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int64, C.c_void_p]
         L.b2d_op_eval_pixel.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_void_p]
         L.b2d_op_histogram.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p]
+        L.b2d_encoder_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]
+        L.b2d_decoder_forward.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.b2d_saturation_count.argtypes = [C.c_int32]
         L.b2d_saturation_count.restype = C.c_uint32
         if L.b2d_abi_version() != 1:

@@ -119,6 +119,9 @@ struct Handle {
     // Time-embedding pipelining inside the reverse loop: d_temb depends on the step index only, so the projections for
     // step i-1 are launched on a side stream as soon as step i's last reader of d_temb has been enqueued, and overlap the
     // final layer + posterior update (a concurrent branch of the captured step graph).
+    // stand-alone Encoder.forward / Decoder.forward (Family R): op range of the decoder and the five feature maps
+    int dec_begin_op = -1;
+    struct Fmap { f16* p; int C, hw; } fmaps[5] = {};
     int temb_free_op = -1;   // index of the first step op after the last reader of d_temb (set by the program builders)
     int temb_t_off = 0;      // added to d_t by the next temb launch (-1 on the side branch)
     cudaStream_t side_stream = nullptr;
@@ -746,6 +749,8 @@ static int build_program_r(Handle* h, int B) {
         cin = cout;
     }
     // ---- Decoder.forward (:512-536), DecoderBlock.forward (:425-460)
+    h->dec_begin_op = (int)ops.v.size();
+    for (int i = 0; i < 5; ++i) h->fmaps[i] = {fmap[i], ENC_CH[i], s[i + 1]};
     const f16* dcur = fmap[4];
     for (int i = 0; i < 4; ++i) {
         const int ci = DEC_IN[i], co = DEC_OUT[i];
@@ -896,7 +901,7 @@ static int ensure_program(Handle* h, int B) {
 // pipelined = inside the reverse loop: op 0 (time embeddings) of this step was produced by the previous step's side branch
 // (or by the loop prologue), and the embeddings of the NEXT step are launched on the side stream at temb_free_op.  The
 // caller joins the side branch (join_temb_side) before it advances the step counter.
-static int run_step_ops(Handle* h, cudaStream_t st, bool pipelined = false) {
+static int run_step_ops(Handle* h, cudaStream_t st, bool pipelined = false, int first = 0, int last = -1) {
     static const bool dbg = getenv("B2D_DEBUG_SYNC") != nullptr;
     static const bool no_pipe = getenv("B2D_NO_TEMB_PIPE") != nullptr;
     static const bool no_branch = getenv("B2D_NO_BRANCH") != nullptr;
@@ -910,7 +915,9 @@ static int run_step_ops(Handle* h, cudaStream_t st, bool pipelined = false) {
     }
     int idx = 0;
     bool branch_open = false;
+    if (last < 0) last = (int)h->step_ops.size();
     for (auto& op : h->step_ops) {
+        if (idx < first || idx >= last) { ++idx; continue; }     // partial programs (stand-alone Encoder / Decoder)
         if (pipe && idx == 0) { ++idx; continue; }
         if (op.side && !no_branch && !dbg) {
             B2D_CUDA(cudaEventRecord(h->ev_br_fork, st));
@@ -1142,6 +1149,75 @@ int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps
     h->cur_eps = eps_out;
     B2D_TRY(run_step_ops(h, st));
     h->last_launches = (int64_t)h->step_ops.size();
+    return 0;
+}
+
+// NHWC f16 <-> NCHW f32 (stand-alone Encoder / Decoder boundaries: the reference hands feature maps around as NCHW fp32)
+__global__ void nhwc_f16_to_nchw_f32_kernel(const f16* __restrict__ in, float* __restrict__ out, int C, int HW, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int p = (int)(i % HW);
+        const int c = (int)((i / HW) % C);
+        const size_t b = i / ((size_t)HW * C);
+        out[i] = __half2float(in[(b * HW + p) * C + c]);
+    }
+}
+__global__ void nchw_f32_to_nhwc_f16_kernel(const float* __restrict__ in, f16* __restrict__ out, int C, int HW, size_t total) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int p = (int)((i / C) % HW);
+        const size_t b = i / ((size_t)HW * C);
+        const float v = in[(b * C + c) * HW + p];
+        if (fabsf(v) > F16_MAX) atomicAdd(&g_sat_count, 1u);
+        out[i] = __float2half_rn(sat_h(v));
+    }
+}
+
+static int upload_t(b2d_handle* h, const int64_t* t_host, int B, cudaStream_t st) {
+    std::vector<int> ti(B);
+    for (int i = 0; i < B; ++i) ti[i] = (int)t_host[i];
+    B2D_CUDA(cudaMemcpyAsync(h->d_t, ti.data(), B * 4, cudaMemcpyHostToDevice, st));
+    B2D_CUDA(cudaStreamSynchronize(st));  // ti is a stack-lifetime staging buffer
+    return 0;
+}
+
+int b2d_encoder_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* const* fmaps_out, int32_t B, void* stream) {
+    B2D_CHECK(h && x && t_host && fmaps_out, "null argument");
+    B2D_CHECK(h->cfg.family == B2D_FAMILY_R, "stand-alone Encoder.forward exists for Family R only");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = as_stream(stream);
+    B2D_TRY(upload_t(h, t_host, B, st));
+    h->cur_x = x;
+    h->cur_eps = h->d_eps;
+    B2D_TRY(run_step_ops(h, st, false, 0, h->dec_begin_op));
+    for (int i = 0; i < 5; ++i) {
+        const Handle::Fmap& f = h->fmaps[i];
+        const size_t total = (size_t)B * f.C * f.hw * f.hw;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+        nhwc_f16_to_nchw_f32_kernel<<<blocks, 256, 0, st>>>(f.p, fmaps_out[i], f.C, f.hw * f.hw, total);
+    }
+    B2D_CUDA(cudaGetLastError());
+    h->last_launches = h->dec_begin_op + 5;
+    return 0;
+}
+
+int b2d_decoder_forward(b2d_handle* h, const float* const* fmaps_in, const int64_t* t_host, float* out, int32_t B, void* stream) {
+    B2D_CHECK(h && fmaps_in && t_host && out, "null argument");
+    B2D_CHECK(h->cfg.family == B2D_FAMILY_R, "stand-alone Decoder.forward exists for Family R only");
+    B2D_TRY(ensure_program(h, B));
+    cudaStream_t st = as_stream(stream);
+    B2D_TRY(upload_t(h, t_host, B, st));
+    for (int i = 0; i < 5; ++i) {
+        const Handle::Fmap& f = h->fmaps[i];
+        const size_t total = (size_t)B * f.C * f.hw * f.hw;
+        const int blocks = (int)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+        nchw_f32_to_nhwc_f16_kernel<<<blocks, 256, 0, st>>>(fmaps_in[i], f.p, f.C, f.hw * f.hw, total);
+    }
+    B2D_CUDA(cudaGetLastError());
+    h->cur_x = h->d_x_work;
+    h->cur_eps = out;
+    B2D_TRY(run_step_ops(h, st, false, 0, 1));                                   // time embeddings + projections
+    B2D_TRY(run_step_ops(h, st, false, h->dec_begin_op, (int)h->step_ops.size()));
+    h->last_launches = (int64_t)h->step_ops.size() - h->dec_begin_op + 6;
     return 0;
 }
 

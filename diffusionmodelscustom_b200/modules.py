@@ -104,8 +104,15 @@ class Encoder(nn.Module):
         if num_classes is not None:
             self.label_emb = nn.Embedding(num_classes, time_embedding)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("Encoder is evaluated only as part of DiffusionNet.forward (fused native program)")
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, t: torch.Tensor, y: Optional[torch.Tensor] = None, cond_img: Optional[torch.Tensor] = None,
+                lsm_cond: Optional[torch.Tensor] = None, topo_cond: Optional[torch.Tensor] = None):
+        """``Encoder.forward`` on its own (modules_DANRA_conditional.py:213-312): returns ``(fmap1, ..., fmap5)`` as fp32 NCHW
+        CUDA tensors.  Runs the encoder half of the native program (b2d_encoder_forward); inside ``DiffusionNet`` the feature maps
+        never leave their fp16 NHWC buffers."""
+        if getattr(self, "_runner", None) is None:
+            object.__setattr__(self, "_runner", _HalfRunner(encoder=self))
+        return self._runner.encode(x, t, y, cond_img, lsm_cond, topo_cond)
 
 
 class DecoderBlock(nn.Module):
@@ -160,8 +167,17 @@ class Decoder(nn.Module):
                                        n_heads=self.n_heads))
         return nn.ModuleList(layers)
 
-    def forward(self, *a, **k):
-        raise NotImplementedError("Decoder is evaluated only as part of DiffusionNet.forward (fused native program)")
+    @torch.no_grad()
+    def forward(self, *fmaps, t: Optional[torch.Tensor] = None):
+        """``Decoder.forward(*fmaps, t=t)`` on its own (modules_DANRA_conditional.py:512-536): five fp32 NCHW CUDA feature maps
+        (fmap1 ... fmap5 in the encoder's order) and the time steps -> the predicted noise (b2d_decoder_forward)."""
+        if len(fmaps) != 5:
+            raise ValueError("Decoder.forward expects the five encoder feature maps")
+        if t is None:
+            raise ValueError("Decoder.forward needs t (the decoder blocks embed it, modules_DANRA_conditional.py:449)")
+        if getattr(self, "_runner", None) is None:
+            object.__setattr__(self, "_runner", _HalfRunner(decoder=self))
+        return self._runner.decode(fmaps, t)
 
 
 class NativeModel(nn.Module):
@@ -212,6 +228,10 @@ class NativeModel(nn.Module):
         """fp32->fp16 conversions clamped at +-65504 since the last reset (0 = the fp16 activation storage never clipped)."""
         return int(N.lib().b2d_saturation_count(int(reset)))
 
+    def _native_state_dict(self):
+        """The reference-keyed state_dict handed to b2d_load_weights (stand-alone Encoder / Decoder runners add placeholders)."""
+        return self.state_dict()
+
     def _release(self):
         if self._h is not None:
             N.lib().b2d_destroy(self._h)
@@ -239,7 +259,7 @@ class NativeModel(nn.Module):
             with torch.cuda.device(device):
                 N.check(L.b2d_create(C.byref(cfg), C.byref(h)))
                 self._h = h
-                sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in self.state_dict().items()
+                sd = {k: v.detach().to("cpu", torch.float32).contiguous() for k, v in self._native_state_dict().items()
                       if v.dtype.is_floating_point}
                 arr = (N.Tensor * len(sd))()
                 for i, (k, v) in enumerate(sd.items()):
@@ -410,6 +430,81 @@ class DiffusionNet(NativeModel):
             N.check(N.lib().b2d_profile_step(h, xx.data_ptr(), th.data_ptr(), B, reps, buf, 512, C.byref(n)))
         return [dict(name=buf[i].name.decode(), klass=buf[i].klass.decode(), flops=buf[i].flops, bytes=buf[i].bytes,
                      ms=buf[i].ms) for i in range(n.value)]
+
+
+class _HalfRunner(DiffusionNet):
+    """Native handle behind a stand-alone ``Encoder`` or ``Decoder``: the other half is a placeholder module (its weights
+    are packed but its ops never run), so the same per-batch program serves ``b2d_encoder_forward`` / ``b2d_decoder_forward``."""
+
+    def __init__(self, encoder: Encoder = None, decoder: Decoder = None):
+        NativeModel.__init__(self)
+        own = encoder if encoder is not None else decoder
+        n_heads = own.n_heads
+        if encoder is None:
+            encoder = Encoder(1, 256, n_heads=n_heads)
+            if isinstance(decoder.residual_layers[0].attention, nn.Module) and hasattr(decoder.residual_layers[0].attention, "ff"):
+                from . import unet as U
+                encoder = U.Encoder(1, 256, n_heads=n_heads, cond_on_lsm=False, cond_on_topo=False)
+        if decoder is None:
+            decoder = Decoder(512, 1, 256, 64, n_heads=n_heads)
+            if hasattr(encoder.attention_layers[0], "ff"):
+                from . import unet as U
+                decoder = U.Decoder(512, 1, 256, 64, n_heads=n_heads)
+        # plain attributes (not registered sub-modules): the stand-alone half must not gain parameters it does not own
+        object.__setattr__(self, "encoder", encoder)
+        object.__setattr__(self, "decoder", decoder)
+        self._attn_ff = int(hasattr(encoder.attention_layers[0], "ff"))
+        own_dev = next(own.parameters()).device
+        (decoder if own is encoder else encoder).to(own_dev)
+
+    def _config(self, img_size, max_batch):
+        cfg = super()._config(img_size, max_batch)
+        cfg.attn_ff = self._attn_ff
+        return cfg
+
+    def _native_state_dict(self):
+        sd = {"encoder." + k: v for k, v in self.encoder.state_dict().items()}
+        sd.update({"decoder." + k: v for k, v in self.decoder.state_dict().items()})
+        return sd
+
+    def _weights_version(self):
+        ts = [t for m in (self.encoder, self.decoder) for t in list(m.parameters()) + list(m.buffers())
+              if t.dtype.is_floating_point and t.numel() > 0]
+        ident = tuple(int(t._version) for t in ts) + tuple(t.data_ptr() for t in ts) + (self._refresh_epoch,)
+        fp = torch.stack(torch._foreach_norm([t.detach() for t in ts])).to("cpu", torch.float64)
+        return ident + (fp.numpy().tobytes(),)
+
+    def encode(self, x, t, y, cond_img, lsm_cond, topo_cond):
+        if x.dim() != 4 or x.shape[-1] != x.shape[-2]:
+            raise ValueError("x must be [B, C, H, H]")
+        B, _, H, _ = x.shape
+        h = self._ensure(B, H, x.device)
+        xx = self._f32c(x, "x")
+        with torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            self._set_conditioning(h, B, y, cond_img, lsm_cond, topo_cond, stream)
+            outs = [torch.full((B, c, H >> (i + 1), H >> (i + 1)), float("nan"), device=x.device, dtype=torch.float32)
+                    for i, c in enumerate(FMAP_CHANNELS)]
+            ptrs = (C.c_void_p * 5)(*[o.data_ptr() for o in outs])
+            th = t.detach().to("cpu", torch.int64).contiguous()
+            N.check(N.lib().b2d_encoder_forward(h, xx.data_ptr(), th.data_ptr(), ptrs, B, stream))
+        return tuple(outs)
+
+    def decode(self, fmaps, t):
+        f1 = fmaps[0]
+        B, H = f1.shape[0], f1.shape[-1] * 2
+        for i, (f, c) in enumerate(zip(fmaps, FMAP_CHANNELS)):
+            if tuple(f.shape) != (B, c, H >> (i + 1), H >> (i + 1)):
+                raise ValueError(f"fmap{i + 1} must be [{B}, {c}, {H >> (i + 1)}, {H >> (i + 1)}], got {tuple(f.shape)}")
+        h = self._ensure(B, H, f1.device)
+        fs = [self._f32c(f, f"fmap{i + 1}") for i, f in enumerate(fmaps)]
+        with torch.cuda.device(f1.device):
+            stream = torch.cuda.current_stream().cuda_stream
+            out = torch.full((B, self.decoder.output_channels, H, H), float("nan"), device=f1.device, dtype=torch.float32)
+            ptrs = (C.c_void_p * 5)(*[f.data_ptr() for f in fs])
+            th = t.detach().to("cpu", torch.int64).contiguous()
+            N.check(N.lib().b2d_decoder_forward(h, ptrs, th.data_ptr(), out.data_ptr(), B, stream))
+        return out
 
 
 # north_star alias: UNet(c_in, c_out, time_dim) style constructor over the same network

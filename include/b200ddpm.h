@@ -86,6 +86,13 @@ int b2d_set_conditioning(b2d_handle* h, const float* lsm, const float* topo, con
 /* One eps_hat = model(x, t, ...) evaluation.  x, eps_out: device fp32 [B,c_hr,H,W]; t: HOST int64 [B]. */
 int b2d_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* eps_out, int32_t B, void* stream);
 
+/* Stand-alone halves of DiffusionNet.forward (Family R), for callers that use Encoder / Decoder on their own
+ * (Encoder.forward modules_DANRA_conditional.py:213-312 returns fmap1..fmap5; Decoder.forward :512-536 takes them and t).
+ * Feature maps cross this boundary as the reference passes them: device fp32 NCHW, [B,64,H/2,H/2] [B,64,H/4,H/4] [B,128,H/8,H/8]
+ * [B,256,H/16,H/16] [B,512,H/32,H/32].  Conditioning for the encoder is whatever b2d_set_conditioning installed. */
+int b2d_encoder_forward(b2d_handle* h, const float* x, const int64_t* t_host, float* const* fmaps_out, int32_t B, void* stream);
+int b2d_decoder_forward(b2d_handle* h, const float* const* fmaps_in, const int64_t* t_host, float* eps_out, int32_t B, void* stream);
+
 /* Whole reverse loop i = T-1 .. 1 on device memory (DiffusionUtils.sample, diffusion_DANRA_conditional.py:127-157).
  * x_inout: device fp32 [B,c_hr,H,W], x_T in / x_0 out.  noise: device fp32 [T][B*c_hr*H*W] host-generated z_i indexed by
  * i (parity runs) or NULL for in-kernel Philox keyed by (seed, sample_offset + sample index, i).

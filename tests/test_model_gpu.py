@@ -280,6 +280,31 @@ def test_in_place_data_update_is_detected():
     assert abs(float((b - a).mean()) - 0.75) < 1e-2
 
 
+def test_standalone_encoder_and_decoder_forward():
+    """Encoder.forward / Decoder.forward on their own (modules_DANRA_conditional.py:213-312, 512-536): the encoder half returns the
+    five feature maps (fp32 NCHW), the decoder half maps five feature maps + t to eps — each against the oracle's intermediates,
+    and chained they reproduce DiffusionNet.forward."""
+    case = dict(R_CASES["full_64_randbn"], batch=3)
+    net, sd = build_ours_r(case)
+    inp, dev = inputs_r(case, 3)
+    t = torch.tensor([999, 40, 500])
+    taps = {}
+    ref = O.family_r_forward(sd, inp["x"], t, inp["y"], inp["cond"], inp["lsm"], inp["topo"], taps=taps)
+    fm = net.encoder(dev["x"], t.cuda(), dev["y"], dev["cond"], dev["lsm"], dev["topo"])
+    assert len(fm) == 5
+    for i, f in enumerate(fm):
+        assert f.dtype == torch.float32 and f.shape == taps[f"fmap{i + 1}"].shape
+        assert G.rel_l2(f, taps[f"fmap{i + 1}"]) < EPS_TOL, i
+    eps_from_ref_maps = net.decoder(*[taps[f"fmap{i + 1}"].cuda() for i in range(5)], t=t.cuda())
+    assert G.rel_l2(eps_from_ref_maps, ref) < EPS_TOL
+    eps_chained = net.decoder(*fm, t=t.cuda())
+    assert G.rel_l2(eps_chained, ref) < EPS_TOL
+    assert G.rel_l2(eps_chained, net(dev["x"], t.cuda(), dev["y"], dev["cond"], dev["lsm"], dev["topo"])) < 2e-3
+    assert "decoder" not in " ".join(net.encoder.state_dict().keys())          # the placeholder half is not registered
+    with pytest.raises(ValueError):
+        net.decoder(*fm[:4], t=t.cuda())
+
+
 # ----------------------------------------------------------------------------------------------- Family D (cfg 4)
 @pytest.mark.parametrize("name", list(D_CASES))
 def test_family_d_eps_vs_reference_golden(name, golden_dir):
