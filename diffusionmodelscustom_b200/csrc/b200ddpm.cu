@@ -17,6 +17,7 @@
 #include "attn_block.cuh"
 #include "common.cuh"
 #include "conv.cuh"
+#include "conv_persist.cuh"
 #include "elementwise.cuh"
 #include "evalops.cuh"
 #include "gemm_stream.cuh"
@@ -494,7 +495,13 @@ struct Builder {
             if (pl->ws_floats) {
                 if (h->alloc(&pl->p.ws, pl->ws_floats) != 0) { err = -2; return; }
             }
-            ops.push_back([pl](cudaStream_t st) { return conv_launch_tc(*pl, st); });
+            if (conv_tcp_eligible(*pl, h->num_sms)) {      // large layers: persistent two-accumulator kernel (conv_persist.cuh)
+                const int sms = h->num_sms;
+                ops.pending.klass = "conv_tc";
+                ops.push_back([pl, sms](cudaStream_t st) { return conv_launch_tcp(*pl, sms, st); });
+            } else {
+                ops.push_back([pl](cudaStream_t st) { return conv_launch_tc(*pl, st); });
+            }
         }
     }
 
@@ -992,6 +999,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
     int rc = 0;
     do {
         if ((rc = conv_tc_init_attrs())) break;
+        if ((rc = conv_tcp_init_attrs())) break;
         if ((rc = flash_attn_init_attrs())) break;
         if ((rc = attn_tc_init_attrs())) break;
         if ((rc = attn_tc2_init_attrs())) break;
@@ -1459,6 +1467,11 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
     }
     B2D_TRY(conv_tc_init_attrs());
     B2D_TRY(conv_plan_build(pl, sms));
+    if (impl == 3 || (impl == 0 && conv_tcp_eligible(pl, sms))) {      // impl 3: force the persistent kernel, 4: the one-tile kernel
+        B2D_CHECK(pl.p.splits == 1, "shape not eligible for the persistent convolution (split-K plan)");
+        B2D_TRY(conv_tcp_init_attrs());
+        return conv_launch_tcp(pl, sms, as_stream(stream));
+    }
     float* ws = nullptr;
     if (pl.ws_floats) {
         B2D_CUDA(cudaMalloc(&ws, pl.ws_floats * sizeof(float)));

@@ -183,9 +183,13 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
         {
             int stage = 0;
             uint32_t phase = 0;
+            // (cb, s, r) advance as counters (one division pair at the start for split-K): two runtime integer divisions per
+            // k-block made this single-thread loop slower (~540 clk per k-block, measured through the persistent variant) than the
+            // tensor core drains a stage (128 clk at BN = 64) — it paced every deep-K launch
+            int tap0 = kb_begin / cblocks;
+            int cb = kb_begin - tap0 * cblocks, r = tap0 / p.S, s = tap0 - r * p.S, tapc = tap0 * p.Cin;
+            const int nbn = nblk * BN;
             for (int kb = kb_begin; kb < kb_end; ++kb) {
-                const int tap = kb / cblocks, cb = kb - tap * cblocks;
-                const int r = tap / p.S, s = tap - r * p.S;
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&full[stage], conv_stage_bytes<BN>());
@@ -199,9 +203,17 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                         const int dh = (hr - ph) >> 1, dw = (wr - pw) >> 1;
                         tma_load_5d(a_dst, &tmA, &full[stage], pw * p.Cin + cb * 64, w0 + dw, ph, h0 + dh, n0);
                     }
-                    tma_load_2d(b_dst, &tmB, &full[stage], tap * p.Cin + cb * 64, nblk * BN);
+                    tma_load_2d(b_dst, &tmB, &full[stage], tapc + cb * 64, nbn);
                 }
                 __syncwarp();
+                if (++cb == cblocks) {
+                    cb = 0;
+                    tapc += p.Cin;
+                    if (++s == p.S) {
+                        s = 0;
+                        ++r;
+                    }
+                }
                 if (++stage == STAGES) {
                     stage = 0;
                     phase ^= 1;

@@ -185,7 +185,9 @@ int b2d_debug_attn_trace(long long* out_host, int32_t max_elems);
 
 /* ---- single operators (unit-test / profiling entry points; all pointers are device memory) ------------------ */
 /* NHWC f16 convolution / projection through the same kernels the model uses.
- * w_packed: f16 [Cout][R*S*Cin] (convt: [(a*2+b)*CoutT+co][Cin]); impl 0 = tcgen05, 1 = CUDA-core cross-check. */
+ * w_packed: f16 [Cout][R*S*Cin] (convt: [(a*2+b)*CoutT+co][Cin]); impl 0 = tcgen05 (kernel chosen as in the model program),
+ * 1 = CUDA-core cross-check, 2 = force the streaming GEMM, 3 = force the persistent two-accumulator convolution,
+ * 4 = force the one-tile-per-CTA convolution. */
 int b2d_op_conv2d(const void* in_f16, const void* w_packed_f16, const float* bias, const void* residual_f16,
                   const float* post_add, int32_t post_stride, void* out_f16, int32_t B, int32_t Hi, int32_t Wi,
                   int32_t Cin, int32_t Cout, int32_t R, int32_t S, int32_t stride, int32_t pad, int32_t convt,

@@ -108,6 +108,48 @@ def test_conv_transpose_matches_torch(shape, impl):
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
 
 
+# Persistent two-accumulator convolution (conv_persist.cuh, impl=3 forces it; needs an un-split plan: >= 75 tiles): several tiles
+# per CTA, both N tilings, stride 2, the 8x8 stem geometry, ragged last tile (TN = 2 images per tile, odd batch), ConvTranspose.
+PERSIST_CASES = [
+    ("p_3x3_c64_32px_b10", 10, 32, 64, 64, 3, 1, 1),
+    ("p_3x3_c128_to256_64px_bn128", 4, 64, 128, 256, 3, 1, 1),
+    ("p_3x3_s2_c64_to128_64px", 6, 64, 64, 128, 3, 2, 1),
+    ("p_8x8_s2_128px", 5, 128, 64, 64, 8, 2, 3),
+    ("p_ragged_8px_b161", 161, 8, 64, 64, 3, 1, 1),
+    ("p_3x3_c64_64px_b40_many_tiles", 40, 64, 64, 64, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_CASES, ids=[c[0] for c in PERSIST_CASES])
+def test_persistent_conv_matches_torch_and_one_tile_kernel(case):
+    _, B, H, Cin, Cout, R, stride, pad = case
+    g = torch.Generator().manual_seed(sum(case[0].encode()))
+    x = _bf(torch.randn(B, Cin, H, H, generator=g))
+    w = _bf(torch.randn(Cout, Cin, R, R, generator=g) / math.sqrt(Cin * R * R))
+    bias = torch.randn(Cout, generator=g)
+    Ho = (H + 2 * pad - R) // stride + 1
+    res = _bf(torch.randn(B, Cout, Ho, Ho, generator=g))
+    vec = torch.randn(B, Cout + 8, generator=g)
+    ref = F.relu(F.conv2d(x, w, bias, stride, pad) + res) + vec[:, :Cout, None, None]
+    args = (G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), G.nhwc_f16(res), vec.cuda(), B, H, H, Cin, Cout, R, stride, pad)
+    out = G.conv2d(*args, act=1, impl=3)
+    assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
+    one = G.conv2d(*args, act=1, impl=4)             # the one-tile-per-CTA kernel: same arithmetic, bit-identical tensor
+    assert torch.equal(out, one)
+
+
+@pytest.mark.parametrize("shape", [(40, 16, 256), (10, 64, 64)])
+def test_persistent_conv_transpose(shape):
+    B, H, C = shape
+    g = torch.Generator().manual_seed(13)
+    x = _bf(torch.randn(B, C, H, H, generator=g))
+    w = _bf(torch.randn(C, C, 2, 2, generator=g) / math.sqrt(C))
+    bias = torch.randn(C, generator=g)
+    ref = F.conv_transpose2d(x, w, bias, stride=2)
+    out = G.conv2d(G.nhwc_f16(x), G.pack_convt_weight(w), bias.cuda(), None, None, B, H, H, C, C, 1, 1, 0, convt=True, impl=3)
+    assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
+
+
 @pytest.mark.parametrize("C", [64, 128, 256, 512])
 def test_layernorm(C):
     g = torch.Generator().manual_seed(C)
