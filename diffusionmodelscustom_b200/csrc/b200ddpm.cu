@@ -1466,7 +1466,8 @@ int b2d_op_conv2d(const void* in, const void* w, const float* bias, const void* 
         return gemm_stream_launch(gp, as_stream(stream));
     }
     B2D_TRY(conv_tc_init_attrs());
-    B2D_TRY(conv_plan_build(pl, sms));
+    B2D_TRY(conv_plan_build(pl, sms, impl != 4 && impl != 5));      // impl 5: persistent kernel without the slab tiling
+    if (impl == 5) impl = 3;
     if (impl == 3 || (impl == 0 && conv_tcp_eligible(pl, sms))) {      // impl 3: force the persistent kernel, 4: the one-tile kernel
         B2D_CHECK(pl.p.splits == 1, "shape not eligible for the persistent convolution (split-K plan)");
         B2D_TRY(conv_tcp_init_attrs());

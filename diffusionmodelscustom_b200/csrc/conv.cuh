@@ -606,13 +606,18 @@ struct ConvPlan {
     int stages = 4;
     dim3 grid;
     bool tc_ready = false;
+    bool slab = false;     // 16 x 8 pixel tiles with (8+2)-row A slabs: only the persistent kernel (conv_persist.cuh) runs such a plan
     size_t ws_floats = 0;  // split-K workspace the caller must provide in p.ws before launching
 };
+inline bool conv_persist_disabled() {
+    static const bool off = getenv("B2D_NO_CONV_PERSIST") != nullptr;
+    return off;
+}
 
 inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // Fills geometry-derived fields of p (tiling) and encodes the tensor maps.
-inline int conv_plan_build(ConvPlan& pl, int num_sms) {
+inline int conv_plan_build(ConvPlan& pl, int num_sms, bool allow_slab = true) {
     ConvParams& p = pl.p;
     B2D_CHECK(p.Cin % 64 == 0, "tcgen05 conv needs Cin % 64 == 0");
     B2D_CHECK(p.Cout % 64 == 0, "tcgen05 conv needs Cout % 64 == 0");
@@ -624,6 +629,20 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     p.TN = 128 / (p.TW * p.TH);
     p.tiles_w = p.Wo / p.TW;
     p.tiles_h = p.Ho / p.TH;
+    // slab tiling for the large 3x3 / stride-1 layers (see conv_persist.cuh): 16 x 8 pixel tiles inside one image
+    static const bool no_slab = getenv("B2D_NO_CONV_SLAB") != nullptr;
+    pl.slab = false;
+    if (allow_slab && !no_slab && !conv_persist_disabled() && !p.convt && p.R == 3 && p.S == 3 && p.stride == 1 && p.pad == 1 &&
+        p.Wo % 16 == 0 && p.Ho % 8 == 0) {
+        const int mt = (p.Wo / 16) * (p.Ho / 8) * p.B;
+        const int nt = (p.Cout % 128 == 0 && mt * (p.Cout / 128) >= num_sms) ? p.Cout / 128 : p.Cout / 64;
+        if (mt * nt >= 2 * num_sms) {
+            pl.slab = true;
+            p.TW = 16; p.TH = 8; p.TN = 1;
+            p.tiles_w = p.Wo / 16;
+            p.tiles_h = p.Ho / 8;
+        }
+    }
     const int mtiles = p.tiles_w * p.tiles_h * ((p.B + p.TN - 1) / p.TN);
     // N tile: 128 only when that still fills the machine and does not straddle a convT sub-pixel block
     int bn = 64;
@@ -648,7 +667,7 @@ inline int conv_plan_build(ConvPlan& pl, int num_sms) {
     if (p.stride == 1) {
         uint64_t dims[4] = {C, W, H, B};
         uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
-        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+        uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)(pl.slab ? p.TH + 2 : p.TH), (uint32_t)p.TN};
         B2D_TRY(make_tmap_f16(&pl.tmA, p.in, 4, dims, str, box));
     } else {
         uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, B};

@@ -21,12 +21,24 @@ namespace b2d {
 constexpr int CONVP_THREADS = 320;
 constexpr int CONVP_EPI_THREADS = 256;
 
-template <int BN, int STAGES>
+// SLAB mode (3x3, stride 1, tiles of 16 x 8 pixels inside one image): the A operand of the three taps of one filter COLUMN is one
+// (8+2)-row x 16-pixel slab, loaded once; tap r is the same shared-memory tile 16 rows (= 2 KB, a multiple of the 1 KB swizzle
+// atom) further down, addressed through the UMMA descriptor.  One ring stage = slab + the three weight tiles of that column.
+// The deep-K layers are bound by the L2 -> shared-memory fill rate (measured 62 B/clk/SM: 430 clk per 24 KB k-block at BN = 64,
+// 515 clk per 32 KB at BN = 128, against 128 / 256 clk of tensor time); the slab cuts the A bytes per filter column from 48 KB to
+// 20 KB.
+constexpr int CONVP_SLAB_TW = 16, CONVP_SLAB_TH = 8;
+constexpr int CONVP_SLAB_A_BYTES = (CONVP_SLAB_TH + 2) * CONVP_SLAB_TW * 128;     // 20 KB
+template <int BN, bool SLAB>
+__host__ __device__ constexpr int convp_stage_bytes() {
+    return SLAB ? CONVP_SLAB_A_BYTES + 3 * BN * 128 : conv_stage_bytes<BN>();
+}
+template <int BN, int STAGES, bool SLAB>
 __host__ __device__ constexpr int convp_smem_bytes() {
-    return STAGES * conv_stage_bytes<BN>() + 2 * (BN / 64) * CONV_A_BYTES /* staging + residual */ + 1024 /*align*/ + 512 /*barriers*/;
+    return STAGES * convp_stage_bytes<BN, SLAB>() + 2 * (BN / 64) * CONV_A_BYTES /* staging + residual */ + 1024 /*align*/ + 512 /*barriers*/;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SLAB>
 __global__ void __launch_bounds__(CONVP_THREADS, 1)
     conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvParams p,
@@ -34,9 +46,11 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
     pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw_p[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_p) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;                                             // STAGES x 16 KB
-    uint8_t* sB = sA + STAGES * CONV_A_BYTES;                       // STAGES x BN*128 B
-    uint8_t* sO = sB + STAGES * (BN * 128);                         // BN/64 staging tiles (128 rows x 128 B, 128B swizzle)
+    constexpr int A_BYTES = SLAB ? CONVP_SLAB_A_BYTES : CONV_A_BYTES;     // per stage
+    constexpr int B_BYTES = SLAB ? 3 * BN * 128 : BN * 128;
+    uint8_t* sA = smem;                                             // STAGES x A_BYTES
+    uint8_t* sB = sA + STAGES * A_BYTES;                            // STAGES x B_BYTES
+    uint8_t* sO = sB + STAGES * B_BYTES;                            // BN/64 staging tiles (128 rows x 128 B, 128B swizzle)
     uint8_t* sR = sO + (BN / 64) * CONV_A_BYTES;                    // BN/64 residual tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (BN / 64) * CONV_A_BYTES);
     uint64_t* full = bars;
@@ -96,10 +110,33 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
             const int mt = t / ntiles, nblk = t - mt * ntiles;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / per_img;
             const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tb * p.TN;
+            const int nbn = nblk * BN;
+            if (SLAB) {
+                // one stage per (channel block, filter column): the slab and the three weight tiles of that column
+                int cb = 0, sc = 0;
+                for (int kk = 0; kk < 3 * cblocks; ++kk) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(&full[stage], (uint32_t)(A_BYTES + B_BYTES));
+                        tma_load_4d(sA + stage * A_BYTES, &tmA, &full[stage], cb * 64, w0 + sc - 1, h0 - 1, n0);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r)
+                            tma_load_2d(sB + stage * B_BYTES + r * (BN * 128), &tmB, &full[stage], (r * 3 + sc) * p.Cin + cb * 64, nbn);
+                    }
+                    __syncwarp();
+                    if (++sc == 3) {
+                        sc = 0;
+                        ++cb;
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            } else {
             // (cb, s, r) advance as counters: the k-block loop must issue faster than the tensor core drains a stage (128 clk for
             // BN = 64), and two runtime integer divisions per k-block alone cost more than that on a single thread
             int cb = 0, s = 0, r = 0, tapc = 0;            // tapc = (r * S + s) * Cin: weight column of the tap
-            const int nbn = nblk * BN;
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (elect_one()) {
@@ -130,6 +167,7 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                     phase ^= 1;
                 }
             }
+            }
             if (p.residual != nullptr) {
                 mbar_wait(res_empty, (it & 1) ^ 1);            // the epilogue has read the previous tile's residual
                 if (elect_one()) {
@@ -158,15 +196,25 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
             const int acc = it & 1;
             mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator stage
             tc_fence_after();
-            for (int kb = 0; kb < num_kb; ++kb) {
+            const int nstage = SLAB ? 3 * cblocks : num_kb;
+            for (int kb = 0; kb < nstage; ++kb) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * CONV_A_BYTES));
-                    const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * (BN * 128)));
+                    const uint64_t da = umma_desc_sw128(smem_u32(sA + stage * A_BYTES));
+                    const uint64_t db = umma_desc_sw128(smem_u32(sB + stage * B_BYTES));
+                    if (SLAB) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_f16(tmem_base + acc * BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        for (int r = 0; r < 3; ++r)              // tap r: the slab 16 rows further down, its own weight tile
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_f16(tmem_base + acc * BN, da + (uint64_t)(r * (CONVP_SLAB_TW * 128 / 16) + k * 2),
+                                         db + (uint64_t)(r * (BN * 128 / 16) + k * 2), idesc, (kb | r | k) != 0);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(tmem_base + acc * BN, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                    }
                     umma_commit(&empty[stage]);
                 }
                 __syncwarp();
@@ -189,6 +237,8 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
         const int lh = (row / p.TW) % p.TH;
         const int ln = row / (p.TW * p.TH);
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        constexpr int NCH_ = BN / 64;
+        int bias_nblk = -1;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -205,8 +255,24 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
             } else {
                 cbase = nblk * BN;
             }
-            float* bias_s = s_bias[it & 1];
-            if (et < BN) bias_s[et] = p.bias ? __ldg(p.bias + cbase + et) : 0.f;
+            // the bias slice only changes with the N block (never, for the many single-N-block layers): no global load per tile
+            float* bias_s = s_bias[0];
+            if (nblk != bias_nblk) {
+                named_bar_sync(1, CONVP_EPI_THREADS);           // every reader of the previous slice is done
+                if (et < BN) bias_s[et] = p.bias ? __ldg(p.bias + cbase + et) : 0.f;
+                bias_nblk = nblk;
+            }
+            // per-sample channel vector (time projection): requested before the accumulator wait, consumed after it
+            float4 pav[NCH_][8];
+            if (p.post_add) {
+#pragma unroll
+                for (int c = 0; c < NCH_; ++c) {
+                    const int ch = (BN == 64) ? g : g * 2 + c;
+                    const float* pa = p.post_add + (size_t)nr * p.post_stride + cbase + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pav[c][j] = __ldg(reinterpret_cast<const float4*>(pa) + j);
+                }
+            }
             // the stores of the previous tile must have read the staging tiles before they are overwritten
             if (et < BN / 64) tma_store_wait_read();            // bulk groups are per thread: the threads that issued the stores wait
             named_bar_sync(1, CONVP_EPI_THREADS);
@@ -225,7 +291,6 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                 tmem_ld32(tmem_base + lane_off + (uint32_t)(acc * BN + ch * 32), v);
                 tmem_ld_wait();
                 uint4* srow = reinterpret_cast<uint4*>(sO + jb * CONV_A_BYTES + row * 128);
-                const int c0 = cbase + ch * 32;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -252,11 +317,10 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                     for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act);
                 }
                 if (p.post_add) {
-                    const float* pa = p.post_add + (size_t)nr * p.post_stride + c0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(pa + j));
-                        f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = pav[c][j];
+                        f[4 * j] += b4.x; f[4 * j + 1] += b4.y; f[4 * j + 2] += b4.z; f[4 * j + 3] += b4.w;
                     }
                 }
                 if (p.gn_partial != nullptr && valid) {
@@ -331,40 +395,47 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SLAB>
 inline int conv_tcp_set_attr() {
-    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, convp_smem_bytes<BN, STAGES>()));
-    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  convp_smem_bytes<BN, STAGES, SLAB>()));
+    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
     return 0;
 }
 inline int conv_tcp_init_attrs() {
-    B2D_TRY((conv_tcp_set_attr<64, 8>()));
-    B2D_TRY((conv_tcp_set_attr<128, 5>()));
+    B2D_TRY((conv_tcp_set_attr<64, 8, false>()));
+    B2D_TRY((conv_tcp_set_attr<128, 5, false>()));
+    B2D_TRY((conv_tcp_set_attr<64, 4, true>()));
+    B2D_TRY((conv_tcp_set_attr<128, 2, true>()));
     return 0;
 }
 
-// Eligible: an un-split plan with enough tiles to give every SM at least two (B2D_NO_CONV_PERSIST disables; min_tiles = 0 forces)
+// Eligible: an un-split plan with enough tiles to give every SM at least two (B2D_NO_CONV_PERSIST disables; a slab plan can only
+// run here)
 inline bool conv_tcp_eligible(const ConvPlan& pl, int num_sms, int min_tiles_per_sm = 2) {
-    static const bool off = getenv("B2D_NO_CONV_PERSIST") != nullptr;
-    if (off || !pl.tc_ready || pl.p.splits != 1) return false;
+    if (!pl.tc_ready || pl.p.splits != 1) return false;
+    if (pl.slab) return true;
+    if (conv_persist_disabled()) return false;
     const int tiles = (int)(pl.grid.x * pl.grid.y);
     return tiles >= min_tiles_per_sm * num_sms;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool SLAB>
 inline int conv_tcp_launch_t(const ConvPlan& pl, int num_sms, cudaStream_t st) {
     const int mtiles = (int)pl.grid.x, ntiles = (int)pl.grid.y;
     const int tiles = mtiles * ntiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    B2D_CUDA(launch_k(conv_tcp_kernel<BN, STAGES>, dim3(grid), dim3(CONVP_THREADS), (size_t)convp_smem_bytes<BN, STAGES>(), st, pl.tmA, pl.tmB,
-                      pl.tmO, pl.tmR, pl.p, mtiles, ntiles));
+    B2D_CUDA(launch_k(conv_tcp_kernel<BN, STAGES, SLAB>, dim3(grid), dim3(CONVP_THREADS), (size_t)convp_smem_bytes<BN, STAGES, SLAB>(), st,
+                      pl.tmA, pl.tmB, pl.tmO, pl.tmR, pl.p, mtiles, ntiles));
     return 0;
 }
 inline int conv_launch_tcp(const ConvPlan& pl, int num_sms, cudaStream_t st) {
     B2D_CHECK(pl.tc_ready && pl.p.splits == 1, "persistent conv needs an un-split plan");
+    if (pl.slab) return pl.bn == 64 ? conv_tcp_launch_t<64, 4, true>(pl, num_sms, st) : conv_tcp_launch_t<128, 2, true>(pl, num_sms, st);
     // deepest rings that fit next to the staging / residual tiles (224 KB): the deep-K layers are paced by the bytes a single
-    // SM keeps in flight (6 -> 8 stages measured on the 8x8 stem-2 convolution: see DESIGN.md)
-    return pl.bn == 64 ? conv_tcp_launch_t<64, 8>(pl, num_sms, st) : conv_tcp_launch_t<128, 5>(pl, num_sms, st);
+    // SM keeps in flight
+    return pl.bn == 64 ? conv_tcp_launch_t<64, 8, false>(pl, num_sms, st) : conv_tcp_launch_t<128, 5, false>(pl, num_sms, st);
 }
 
 }  // namespace b2d

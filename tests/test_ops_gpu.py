@@ -116,7 +116,10 @@ PERSIST_CASES = [
     ("p_3x3_s2_c64_to128_64px", 6, 64, 64, 128, 3, 2, 1),
     ("p_8x8_s2_128px", 5, 128, 64, 64, 8, 2, 3),
     ("p_ragged_8px_b161", 161, 8, 64, 64, 3, 1, 1),
-    ("p_3x3_c64_64px_b40_many_tiles", 40, 64, 64, 64, 3, 1, 1),
+    ("p_3x3_c64_64px_b40_many_tiles", 40, 64, 64, 64, 3, 1, 1),          # slab tiling (16 x 8 pixel tiles), BN = 64
+    ("p_slab_c128_to256_32px_b24", 24, 32, 128, 256, 3, 1, 1),           # slab tiling, BN = 128
+    ("p_slab_c256_16px_b160_deepK", 160, 16, 256, 256, 3, 1, 1),         # slab tiling, 12 ring stages per tile
+    ("p_slab_c64_128px_b3", 3, 128, 64, 64, 3, 1, 1),
 ]
 
 
@@ -132,10 +135,12 @@ def test_persistent_conv_matches_torch_and_one_tile_kernel(case):
     vec = torch.randn(B, Cout + 8, generator=g)
     ref = F.relu(F.conv2d(x, w, bias, stride, pad) + res) + vec[:, :Cout, None, None]
     args = (G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), G.nhwc_f16(res), vec.cuda(), B, H, H, Cin, Cout, R, stride, pad)
-    out = G.conv2d(*args, act=1, impl=3)
+    out = G.conv2d(*args, act=1, impl=3)             # persistent kernel, slab tiling where the plan chooses it
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
-    one = G.conv2d(*args, act=1, impl=4)             # the one-tile-per-CTA kernel: same arithmetic, bit-identical tensor
-    assert torch.equal(out, one)
+    one = G.conv2d(*args, act=1, impl=4)             # the one-tile-per-CTA kernel
+    noslab = G.conv2d(*args, act=1, impl=5)          # persistent kernel without the slab tiling: same K order as the one-tile kernel
+    assert torch.equal(noslab, one)
+    assert G.rel_l2(out.float(), one.float()) < 1e-3  # the slab walks K in (channel block, column, row) order
 
 
 @pytest.mark.parametrize("shape", [(40, 16, 256), (10, 64, 64)])
