@@ -1,5 +1,5 @@
 """GPU bring-up report (not a test): runs each kernel class and the model with per-layer taps, printing errors instead of
-asserting, so that one gpurun call localises every problem.  Usage on the GPU box: python tools_bringup.py"""
+asserting, so that one gpurun call localises every problem.  Usage on the GPU box: python tools/bringup.py"""
 import math
 import sys
 import traceback
@@ -11,8 +11,8 @@ sys.path.insert(0, ".")
 from diffusionmodelscustom_b200 import _native as N   # noqa: E402
 from oracle import ddpm_oracle as O                   # noqa: E402
 from tests import gpu_util as G                       # noqa: E402
-from tests.cases import R_CASES                       # noqa: E402
-from tests.model_util import build_ours_r, inputs_r   # noqa: E402
+from diffusionmodelscustom_b200.configs import R_CASES                       # noqa: E402
+from diffusionmodelscustom_b200.configs import build_ours_r, inputs_r   # noqa: E402
 
 
 def bf(x):
@@ -69,8 +69,8 @@ def main():
 
 
 def family_d():
-    from tests.cases import D_CASES
-    from tests.model_util import build_ours_d, inputs_d
+    from diffusionmodelscustom_b200.configs import D_CASES
+    from diffusionmodelscustom_b200.configs import build_ours_d, inputs_d
     case = D_CASES["cfg4_downscale_64"]
     for simt in (True, False):
         def model():
