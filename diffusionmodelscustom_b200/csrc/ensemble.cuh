@@ -68,7 +68,7 @@ static int ensemble_resources(b2d_handle* h, int sub_batch, size_t cond_row_elem
 extern "C" {
 
 int b2d_ensemble_run(b2d_handle* h, const b2d_ensemble_job* job, b2d_ensemble_stats* stats) {
-    B2D_CHECK(h && job && job->out, "null argument");
+    B2D_CHECK(h && job && (job->out || job->count == 0), "null argument");
     B2D_CHECK(h->T >= 2, "b2d_set_schedule has not been called");
     const b2d_config& c = h->cfg;
     B2D_CHECK(job->n_dates >= 1 && job->members >= 1 && job->sub_batch >= 1, "bad ensemble shape");
