@@ -14,6 +14,7 @@
 #include "attention_tc.cuh"
 #include "attention_tc2.cuh"
 #include "attention_tc3.cuh"
+#include "attention_tc3d32.cuh"
 #include "attn_block.cuh"
 #include "common.cuh"
 #include "conv.cuh"
@@ -573,6 +574,11 @@ struct Builder {
                 ops.push_back([=](cudaStream_t st) { return attn_tc4_launch(*tm4, ao, Bc, L, C, heads, st); });
             } else
                 ops.push_back([=](cudaStream_t st) { return attn_tc3_launch(*tmq, ao, Bc, L, C, heads, st); });
+        } else if (attn_tc5_supported(L, C, heads) && !no_tc_attn) {     // head_dim 32 on tcgen05 (attention_tc3d32.cuh)
+            auto tm5 = std::make_shared<AttnTcMaps>();
+            if (attn_tc5_make_map(tm5.get(), qkv, B, L, C) != 0) { err = -1; return; }
+            ops.meta(role + ".sdpa", "attn_tc32", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
+            ops.push_back([=](cudaStream_t st) { return attn_tc5_launch(*tm5, ao, Bc, L, C, heads, st); });
         } else {
             ops.meta(role + ".sdpa", "flash_attn", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
             ops.push_back([=](cudaStream_t st) { return flash_attn_launch(qkv, ao, Bc, L, C, heads, st); });
@@ -1004,6 +1010,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = attn_tc_init_attrs())) break;
         if ((rc = attn_tc2_init_attrs())) break;
         if ((rc = attn_tc3_init_attrs())) break;
+        if ((rc = attn_tc5_init_attrs())) break;
         if ((rc = gemm_stream_init_attrs())) break;
         if ((rc = attn_block_init_attrs())) break;
         if ((rc = norm_fused_init_attrs())) break;
@@ -1514,6 +1521,12 @@ int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, 
             return attn_tc2_launch(tm, (f16*)o, B, L, C, heads, sms, as_stream(stream));
         }
         return attn_tc_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
+    }
+    if (attn_tc5_supported(L, C, heads) && getenv("B2D_NO_TC_ATTN") == nullptr) {
+        B2D_TRY(attn_tc5_init_attrs());
+        AttnTcMaps tm5;
+        B2D_TRY(attn_tc5_make_map(&tm5, (const f16*)qkv, B, L, C));
+        return attn_tc5_launch(tm5, (f16*)o, B, L, C, heads, as_stream(stream));
     }
     return flash_attn_launch((const f16*)qkv, (f16*)o, B, L, C, heads, as_stream(stream));
 }

@@ -171,7 +171,9 @@ def test_layernorm(C):
 ATTN_CASES = [(2, 1024, 64, 4), (2, 256, 64, 4), (3, 64, 128, 4), (3, 16, 256, 4), (5, 4, 512, 4), (2, 1, 512, 4),
               (2, 100, 64, 4), (2, 256, 64, 8), (1, 64, 128, 32), (2, 4096, 64, 4), (2, 16, 128, 1),
               # n_heads = 1 (launcher default of the clean application): head_dim = C up to 512
-              (3, 16, 256, 1), (3, 64, 256, 1), (5, 4, 512, 1), (2, 16, 512, 1), (2, 1024, 64, 1), (2, 256, 64, 1)]
+              (3, 16, 256, 1), (3, 64, 256, 1), (5, 4, 512, 1), (2, 16, 512, 1), (2, 1024, 64, 1), (2, 256, 64, 1),
+              # head_dim 32 on tcgen05 (attention_tc3d32.cuh): C = 128 with 4 heads, 256 with 8
+              (2, 1024, 128, 4), (3, 256, 128, 4), (1, 128, 256, 8), (9, 512, 128, 4)]
 
 
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}" for b, l, c, h in ATTN_CASES])
@@ -193,7 +195,8 @@ def test_attention_matches_torch(case):
 # read-out / re-initialisation), and PEAKY score distributions (q, k scaled up: row maxima that keep growing across key blocks
 # => lazy-reference moves with O rescaled in TMEM; scores far below the maximum => the packed-half polynomial path must flush
 # to zero exactly like the SFU path).
-ATTN_TC2_CASES = [(37, 1024, 64, 4, 1.0), (3, 1024, 64, 4, 3.0), (2, 4096, 64, 4, 2.5), (1, 256, 64, 4, 4.0), (150, 256, 64, 4, 1.5)]
+ATTN_TC2_CASES = [(37, 1024, 64, 4, 1.0), (3, 1024, 64, 4, 3.0), (2, 4096, 64, 4, 2.5), (1, 256, 64, 4, 4.0), (150, 256, 64, 4, 1.5),
+                  (3, 1024, 128, 4, 2.5), (2, 256, 128, 4, 4.0)]      # head_dim 32, peaky
 
 
 @pytest.mark.parametrize("case", ATTN_TC2_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}_x{s}" for b, l, c, h, s in ATTN_TC2_CASES])
