@@ -15,6 +15,8 @@
 #include "attention_tc2.cuh"
 #include "attention_tc3.cuh"
 #include "attention_tc3d32.cuh"
+#include "attention_tc6.cuh"
+#include "attention_tc8.cuh"
 #include "attn_block.cuh"
 #include "common.cuh"
 #include "conv.cuh"
@@ -562,7 +564,7 @@ struct Builder {
             ops.meta(role + ".sdpa", "attn_tc", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
             // B2D_ATTN_V=1: round-1 kernel (3 CTAs/SM); 2: persistent two-tile kernel (attention_tc2.cuh); default 3: the
             // four-CTAs-per-SM optimistic-maximum kernel (attention_tc3.cuh) — A/B switches, all three are parity-tested
-            static const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 3;
+            static const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 8;
             const int sms = h->num_sms;
             if (attn_v == 2 && attn_tc2_supported(L, C, heads))
                 ops.push_back([=](cudaStream_t st) { return attn_tc2_launch(*tmq, ao, Bc, L, C, heads, sms, st); });
@@ -572,7 +574,13 @@ struct Builder {
                 auto tm4 = std::make_shared<AttnTcMaps>();
                 if (attn_tc4_make_map(tm4.get(), qkv, B, L, C) != 0) { err = -1; return; }
                 ops.push_back([=](cudaStream_t st) { return attn_tc4_launch(*tm4, ao, Bc, L, C, heads, st); });
-            } else
+            } else if (attn_v == 6)
+                ops.push_back([=](cudaStream_t st) { return attn_tc6_launch<0>(*tmq, ao, Bc, L, C, heads, st); });
+            else if (attn_v == 7)
+                ops.push_back([=](cudaStream_t st) { return attn_tc6_launch<1>(*tmq, ao, Bc, L, C, heads, st); });
+            else if (attn_v == 8)
+                ops.push_back([=](cudaStream_t st) { return attn_tc8_launch(*tmq, ao, Bc, L, C, heads, st); });
+            else
                 ops.push_back([=](cudaStream_t st) { return attn_tc3_launch(*tmq, ao, Bc, L, C, heads, st); });
         } else if (attn_tc5_supported(L, C, heads) && !no_tc_attn) {     // head_dim 32 on tcgen05 (attention_tc3d32.cuh)
             auto tm5 = std::make_shared<AttnTcMaps>();
@@ -1011,6 +1019,8 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = attn_tc2_init_attrs())) break;
         if ((rc = attn_tc3_init_attrs())) break;
         if ((rc = attn_tc5_init_attrs())) break;
+        if ((rc = attn_tc6_init_attrs())) break;
+        if ((rc = attn_tc8_init_attrs())) break;
         if ((rc = gemm_stream_init_attrs())) break;
         if ((rc = attn_block_init_attrs())) break;
         if ((rc = norm_fused_init_attrs())) break;
@@ -1503,10 +1513,19 @@ int b2d_op_attention(const void* qkv, void* o, int32_t B, int32_t L, int32_t C, 
         B2D_TRY(attn_tc_init_attrs());
         AttnTcMaps tm;
         B2D_TRY(attn_tc_make_map(&tm, (const f16*)qkv, B, L, C));
-        const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 3;
+        const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 8;
         if (attn_v == 3) {
             B2D_TRY(attn_tc3_init_attrs());
             return attn_tc3_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
+        }
+        if (attn_v == 8) {
+            B2D_TRY(attn_tc8_init_attrs());
+            return attn_tc8_launch(tm, (f16*)o, B, L, C, heads, as_stream(stream));
+        }
+        if (attn_v == 6 || attn_v == 7) {
+            B2D_TRY(attn_tc6_init_attrs());
+            return attn_v == 6 ? attn_tc6_launch<0>(tm, (f16*)o, B, L, C, heads, as_stream(stream))
+                               : attn_tc6_launch<1>(tm, (f16*)o, B, L, C, heads, as_stream(stream));
         }
         if (attn_v == 4) {
             B2D_TRY(attn_tc3_init_attrs());
