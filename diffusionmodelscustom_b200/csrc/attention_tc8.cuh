@@ -11,6 +11,12 @@
 // thread's next named-barrier arrival (which is what releases the next S MMA).  A half whose MMA was issued BEFORE a move carries
 // the old reference; the thread remembers the value baked into each in-flight half and subtracts the difference in the (rare)
 // slow path.  m_ref is kept equal to hi + lo exactly, so what the tensor core subtracts is what the bookkeeping assumes.
+// The same MMA step adds a PER-COLUMN constant (E_q column 2 is 1, E_k column 2 holds it): P is stored as p * 2^7 (the factor
+// cancels in O / l; 2^8 * 2^7 still fits fp16 and the flush point moves from 2^-15 down to 2^-22), so SFU columns receive x + 7 and
+// polynomial columns x + 22, which is what lets the converter's own relu clamp stand in for the lower clamp of the exponent
+// range: a polynomial pair costs 10 instructions.
+// Tried on top of this and measured slower (kept out): P.V issued per 32-key half with its own barrier (460 vs 456 us at B=32,
+// L=4096: the P buffer is not what couples the warps), polynomial and SFU pairs alternating one by one (463 us).
 #pragma once
 #include "attention_tc6.cuh"
 
@@ -21,18 +27,21 @@ constexpr int AT8_EQ_BYTES = ATC_BLK * ATC_D * 2;             // 4 KB
 constexpr int AT8_EK_BYTES = (ATC_BN / 2) * ATC_D * 2;        // 1 KB
 constexpr int AT8_SMEM = 1024 + ATC_TILE_BYTES + ATC_KV_BYTES * 3 * ATC_STAGES + AT8_EQ_BYTES + AT8_EK_BYTES + 256;
 
-// 2^x for a pair of fp32 arguments x <= ~16 on the FMA pipe in packed half precision; x <= -15 flushes to +0 exactly
-__device__ __forceinline__ uint32_t ex2_pair_poly_neg(float xa, float xb) {
+constexpr float AT8_OFF_SFU = 7.0f, AT8_OFF_POLY = 22.0f;     // per-column constants added by the tensor core (log2 units)
+
+// 2^(x' - 15) for a pair of fp32 arguments x' in (-inf, 30] on the FMA pipe in packed half precision; x' <= 0 flushes to +0 exactly
+__device__ __forceinline__ uint32_t ex2_pair_poly_off(float xa, float xb) {
     uint32_t h, xr, nf, f, p, r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(xb), "f"(xa));                   // low half <- xa
-    asm("max.f16x2 %0, %1, %2;" : "=r"(h) : "r"(h), "r"(0xCB80CB80u));                   // clamp at -15
-    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(xr) : "r"(h), "r"(0x660F660Fu));              // + 1551: (n + 15) lands in the mantissa
-    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(nf) : "r"(xr), "r"(0x660F660Fu));             // n as a half
+    asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(xb), "f"(xa));             // low half <- xa; negative -> +0
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(xr) : "r"(h), "r"(0x66006600u));              // + 1536: integer part lands in the mantissa
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(nf) : "r"(xr), "r"(0x66006600u));             // n' as a half
     asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(f) : "r"(h), "r"(nf));                        // f in [-0.5, 0.5]
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(0x2B0D2B0Du), "r"(f), "r"(0x33C333C3u));   // 0.05509 f + 0.24260
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(p), "r"(f), "r"(0x398C398Cu));              // .. f + 0.69328
     asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(p), "r"(f), "r"(0x3C003C00u));              // .. f + 1
-    const uint32_t e = (xr << 10) & 0x7C007C00u;                                         // 2^n as half bits; n = -15 -> +0.0
+    // 2^(n' - 15) as half bits in ONE integer multiply-add: xr << 10 puts n' (mantissa bits 0..4, n' <= 31) into each exponent
+    // field; what the low half spills into the high half's mantissa is the constant 0x6600 >> 6, subtracted again.  n' = 0 -> +0.0
+    const uint32_t e = xr * 1024u - 0x01980000u;
     asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(p), "r"(e));
     return r;
 }
@@ -77,8 +86,13 @@ __global__ void __launch_bounds__(AT8_THREADS, AT6_CTAS_PER_SM)
         const int st = i / (ATC_BN * 2), r = i % (ATC_BN * 2);
         *reinterpret_cast<uint4*>(sV + st * 2 * ATC_KV_BYTES + ATC_KV_BYTES + r * 16) = make_uint4(0x00003C00u, 0u, 0u, 0u);
     }
-    for (int i = threadIdx.x; i < AT8_EQ_BYTES / 16; i += NT) *reinterpret_cast<uint4*>(sEq + i * 16) = make_uint4(0u, 0u, 0u, 0u);
-    for (int i = threadIdx.x; i < AT8_EK_BYTES / 16; i += NT) *reinterpret_cast<uint4*>(sEk + i * 16) = make_uint4(0x38003800u, 0u, 0u, 0u);
+    // E_q rows [0, 0, 1, 0.. | same]; E_k row c [.5, .5, off_c / 2, 0.. | same] (every term enters twice: once per 16-byte half)
+    for (int i = threadIdx.x; i < AT8_EQ_BYTES / 16; i += NT) *reinterpret_cast<uint4*>(sEq + i * 16) = make_uint4(0u, 0x00003C00u, 0u, 0u);
+    for (int i = threadIdx.x; i < AT8_EK_BYTES / 16; i += NT) {
+        const int pair = (i >> 1) >> 1;                                  // S column = E_k row = i >> 1; two columns per fp16 pair
+        const uint32_t half_off = ((pair & 7) < POLY) ? 0x4980u /* 11 */ : 0x4300u /* 3.5 */;
+        *reinterpret_cast<uint4*>(sEk + i * 16) = make_uint4(0x38003800u, half_off, 0u, 0u);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -204,11 +218,13 @@ __global__ void __launch_bounds__(AT8_THREADS, AT6_CTAS_PER_SM)
                 named_bar_arrive(1 + ch, NT);                    // releases this half: S_{j+1} is issued with E_q as it is NOW
                 const float d0 = m_ref - mb[ch];                 // this half was issued d0 ago (0 unless the reference moved since)
                 mb[ch] = m_eq;
-                float mx[2] = {-INFINITY, -INFINITY};
+                float mx[2] = {-INFINITY, -INFINITY};            // [0]: SFU columns (x + 7), [1]: polynomial columns (x + 22)
 #pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    mx[(i >> 1) & 1] = fmaxf(mx[(i >> 1) & 1], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-                const float cm = fmaxf(mx[0], mx[1]) - d0;       // maximum of the half relative to m_ref
+                for (int i = 0; i < 32; i += 2) {
+                    const int cls = (((i >> 1) & 7) < POLY) ? 1 : 0;
+                    mx[cls] = fmaxf(mx[cls], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+                }
+                const float cm = fmaxf(mx[0] - AT8_OFF_SFU, mx[1] - AT8_OFF_POLY) - d0;   // maximum of the half relative to m_ref
                 const bool first = (j == 0) && (ch == 0);
                 const bool move = cm > 8.0f || first;
                 if (__any_sync(0xffffffffu, move || d0 != 0.0f)) {           // rare after the first blocks
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(AT8_THREADS, AT6_CTAS_PER_SM)
                     if (idx < 16) {
                         const float s0 = __uint_as_float(v[2 * idx]), s1 = __uint_as_float(v[2 * idx + 1]);
                         if ((idx & 7) < POLY) {
-                            pk[idx] = ex2_pair_poly_neg(s0, s1);
+                            pk[idx] = ex2_pair_poly_off(s0, s1);
                         } else {
                             v[2 * idx] = __float_as_uint(ex2_ordered(s0));
                             v[2 * idx + 1] = __float_as_uint(ex2_ordered(s1));
