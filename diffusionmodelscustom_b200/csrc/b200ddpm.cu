@@ -25,6 +25,7 @@
 #include "evalops.cuh"
 #include "gemm_stream.cuh"
 #include "norm_fused.cuh"
+#include "tail_tc.cuh"
 
 namespace b2d {
 thread_local Status g_status;
@@ -811,9 +812,15 @@ static int build_program_r(Handle* h, int B) {
         const float* twk = bd.W<float>("tail.wk");
         const int cout = c.c_out, Hh = H;
         ops.meta("final.conv", "tail_conv", 2.0 * B * Hh * Hh * 576 * cout, (double)B * Hh * Hh * (64 * 2 + 4 * cout));
+        static const bool no_tc_tail = getenv("B2D_NO_TC_TAIL") != nullptr;
+        auto ttp = std::make_shared<TailTcPlan>();
+        const bool tc_tail = tail_tc_supported(Hh, Hh, cout) && !no_tc_tail;
+        if (tc_tail && tail_tc_plan_build(*ttp, up, B, Hh, Hh) != 0) return g_status.code ? g_status.code : fail(-1, "tail plan failed");
         ops.push_back([=](cudaStream_t s2) {
             dim3 grid((Hh + 31) / 32, (Hh + 7) / 8, B);
             static const bool simt_tail = getenv("B2D_SIMT_TAIL") != nullptr;
+            if (tc_tail)
+                return tail_tc_launch(*ttp, st, twk, tb, hh->cur_eps, Hh, Hh, s2);
             if (cout <= 8 && !simt_tail)
                 B2D_CUDA(launch_k(tail_mma_kernel, dim3(grid), dim3(256), TAILM_SMEM, s2, up, st, twk, tb, hh->cur_eps, Hh, Hh, cout));
             else
@@ -1021,6 +1028,7 @@ int b2d_create(const b2d_config* cfg, b2d_handle** out) {
         if ((rc = attn_tc5_init_attrs())) break;
         if ((rc = attn_tc6_init_attrs())) break;
         if ((rc = attn_tc8_init_attrs())) break;
+        if ((rc = tail_tc_init_attrs())) break;
         if ((rc = gemm_stream_init_attrs())) break;
         if ((rc = attn_block_init_attrs())) break;
         if ((rc = norm_fused_init_attrs())) break;
