@@ -116,7 +116,24 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t u) {
     return __half22float2(v);
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// nn.GELU() (erf form) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf; measured <= 4.7e-7 absolute on the GELU
+// against float64 over [-12, 12]): 15 instructions with one MUFU.RCP and one MUFU.EX2 and no branch, against ~30 for erff().
+// The GroupNorm-apply passes of Family D are issue-bound on exactly this function.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float az = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+    const float er = copysignf(fmaf(-p, e, 1.0f), x);
+    const float hx = 0.5f * x;
+    return fmaf(hx, er, hx);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 // ---------------------------------------------------------------- mbarrier / TMA / tcgen05 PTX

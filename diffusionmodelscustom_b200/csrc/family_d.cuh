@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(256) sample_stats_kernel(const f16* __restrict
 // Statistics come either from stats[b] = {mean, rstd} (sample_stats_kernel) or from the per-tile {sum, sumsq} partials the
 // producing convolution wrote in its epilogue (gn_partial: [ntiles][mtiles][2], sample b owns m-tiles [b*tps, (b+1)*tps)):
 // every CTA of sample b adds them in the same fixed order.  grid = (chunks, B).
+constexpr int GNA_ITER = 4;
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const f16* __restrict__ x, const float* __restrict__ stats,
                                                               const float* __restrict__ gn_partial, int tps, int ntiles, int mtiles,
                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -178,37 +179,59 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const f16* __restr
     __syncthreads();
     const float mean = s_ms[0], rstd = s_ms[1];
     const size_t n8 = per_sample / 8;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t e = (size_t)b * per_sample + i * 8;
-        const int c = (int)((i * 8) % C);
-        const uint4 xv = *reinterpret_cast<const uint4*>(x + e);
-        float f[8];
-        float2 t;
-        t = unpack_h2(xv.x); f[0] = t.x; f[1] = t.y;
-        t = unpack_h2(xv.y); f[2] = t.x; f[3] = t.y;
-        t = unpack_h2(xv.z); f[4] = t.x; f[5] = t.y;
-        t = unpack_h2(xv.w); f[6] = t.x; f[7] = t.y;
+    // Every CTA covers GNA_ITER * 256 consecutive 16-byte vectors; 256 * 8 elements are a multiple of C (checked on the host), so
+    // a thread's eight channels are the same in every iteration: gamma / beta are folded once into  y = a * x + c,
+    // and all of the thread's loads are issued before the (GELU-heavy) arithmetic starts.
+    const int c = (int)((threadIdx.x * 8) % C);
+    float aa[8], cc[8];
+    {
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
         const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
         const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
+        for (int j = 0; j < 8; ++j) {
+            aa[j] = rstd * gg[j];
+            cc[j] = fmaf(-mean, aa[j], bb[j]);
+            if (vec) cc[j] += act == 2 ? 0.f : vec[(size_t)b * vec_stride + c + j];   // the vector is added AFTER the activation
+        }
+    }
+    float vv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) vv[j] = (vec && act == 2) ? vec[(size_t)b * vec_stride + c + j] : 0.f;
+    const size_t i0 = (size_t)blockIdx.x * (GNA_ITER * 256) + threadIdx.x;
+    uint4 xv[GNA_ITER], rv[GNA_ITER];
+#pragma unroll
+    for (int it = 0; it < GNA_ITER; ++it) {
+        const size_t i = i0 + (size_t)it * 256;
+        if (i < n8) {
+            const size_t e = (size_t)b * per_sample + i * 8;
+            xv[it] = *reinterpret_cast<const uint4*>(x + e);
+            if (res) rv[it] = *reinterpret_cast<const uint4*>(res + e);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < GNA_ITER; ++it) {
+        const size_t i = i0 + (size_t)it * 256;
+        if (i >= n8) break;
+        const size_t e = (size_t)b * per_sample + i * 8;
+        float f[8];
+        float2 t;
+        t = unpack_h2(xv[it].x); f[0] = t.x; f[1] = t.y;
+        t = unpack_h2(xv[it].y); f[2] = t.x; f[3] = t.y;
+        t = unpack_h2(xv[it].z); f[4] = t.x; f[5] = t.y;
+        t = unpack_h2(xv[it].w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], aa[j], cc[j]);
         if (res) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(res + e);
-            t = unpack_h2(rv.x); f[0] += t.x; f[1] += t.y;
-            t = unpack_h2(rv.y); f[2] += t.x; f[3] += t.y;
-            t = unpack_h2(rv.z); f[4] += t.x; f[5] += t.y;
-            t = unpack_h2(rv.w); f[6] += t.x; f[7] += t.y;
+            t = unpack_h2(rv[it].x); f[0] += t.x; f[1] += t.y;
+            t = unpack_h2(rv[it].y); f[2] += t.x; f[3] += t.y;
+            t = unpack_h2(rv[it].z); f[4] += t.x; f[5] += t.y;
+            t = unpack_h2(rv[it].w); f[6] += t.x; f[7] += t.y;
         }
         if (act == 2) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (vec) {
-            const float* vp = vec + (size_t)b * vec_stride + c;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += vp[j];
+            for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]) + vv[j];
         }
         uint4 o;
         o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
@@ -435,9 +458,10 @@ struct BuilderD : Builder {
         const float* b = W<float>(gnrole + ".b");
         const size_t n8 = per_sample / 8;
         const int Bc = B;
+        if (2048 % C != 0) { err = -1; fail(-1, "groupnorm_apply: 2048 must be a multiple of the channel count"); return; }
         ops.meta("gn_apply", "groupnorm_apply", 0, 2.0 * B * per_sample * (res ? 3 : 2));
         ops.push_back([=](cudaStream_t s) {
-            int chunks = (int)std::min<size_t>((n8 + 255) / 256, (size_t)std::max(1, 148 * 16 / Bc));
+            const int chunks = (int)((n8 + GNA_ITER * 256 - 1) / (GNA_ITER * 256));
             B2D_CUDA(launch_k(groupnorm_apply_kernel, dim3(chunks, Bc), dim3(256), 0, s, x, st, partial, tps, ntiles, mtiles, g, b,
                               res, act, vec, vec_stride, y, per_sample, C));
             return 0;
