@@ -335,7 +335,9 @@ def class_rooflines(prof, pk):
             texp = k["flops"] / (4.0 * HEAD_DIM_OF_CLASS[name]) / sec / 1e12
             e.update(bound="tensor", achieved=tf, peak=pk["tf_burst"], unit="TFLOP/s", frac=tf / pk["tf_burst"],
                      co_bound={"bound": "sfu_ex2", "achieved": texp, "peak": SFU_PEAK_TEXP, "unit": "Texp/s",
-                               "frac": texp / SFU_PEAK_TEXP, "peak_source": "tools/ub/mufu.cu measured on this pool"})
+                               "frac": texp / SFU_PEAK_TEXP, "peak_source": "tools/ub/mufu.cu measured on this pool",
+                               "note": "peak = every exponential on the SFU; the kernel evaluates half of them on the FMA pipe "
+                                       "(packed-half polynomial), so frac may exceed 1 — the kernel is issue-bound, see profiles/"})
         elif k["flops"] and k["flops"] / max(k["bytes"], 1.0) > 150.0:   # above ~260 FLOP/B the tensor pipe is the roof; 150 keeps conv/attn blocks there
             e.update(bound="tensor", achieved=tf, peak=pk["tf_burst"], unit="TFLOP/s", frac=tf / pk["tf_burst"])
         else:

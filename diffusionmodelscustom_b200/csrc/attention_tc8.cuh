@@ -224,10 +224,12 @@ __global__ void __launch_bounds__(AT8_THREADS, AT6_CTAS_PER_SM)
                     const int cls = (((i >> 1) & 7) < POLY) ? 1 : 0;
                     mx[cls] = fmaxf(mx[cls], fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
                 }
-                const float cm = fmaxf(mx[0] - AT8_OFF_SFU, mx[1] - AT8_OFF_POLY) - d0;   // maximum of the half relative to m_ref
                 const bool first = (j == 0) && (ch == 0);
-                const bool move = cm > 8.0f || first;
-                if (__any_sync(0xffffffffu, move || d0 != 0.0f)) {           // rare after the first blocks
+                // fast-path test without forming the maximum: with d0 == 0 the class maxima are relative to m_ref already
+                const bool slow = d0 != 0.0f || mx[0] > 8.0f + AT8_OFF_SFU || mx[1] > 8.0f + AT8_OFF_POLY || first;
+                if (__any_sync(0xffffffffu, slow)) {                         // rare after the first blocks
+                    const float cm = fmaxf(mx[0] - AT8_OFF_SFU, mx[1] - AT8_OFF_POLY) - d0;   // maximum of the half relative to m_ref
+                    const bool move = cm > 8.0f || first;
                     float m_new = m_ref;
                     if (move) {                                  // new reference, exactly representable as hi + lo
                         const float t = m_ref + cm;

@@ -173,7 +173,9 @@ ATTN_CASES = [(2, 1024, 64, 4), (2, 256, 64, 4), (3, 64, 128, 4), (3, 16, 256, 4
               # n_heads = 1 (launcher default of the clean application): head_dim = C up to 512
               (3, 16, 256, 1), (3, 64, 256, 1), (5, 4, 512, 1), (2, 16, 512, 1), (2, 1024, 64, 1), (2, 256, 64, 1),
               # head_dim 32 on tcgen05 (attention_tc3d32.cuh): C = 128 with 4 heads, 256 with 8
-              (2, 1024, 128, 4), (3, 256, 128, 4), (1, 128, 256, 8), (9, 512, 128, 4)]
+              (2, 1024, 128, 4), (3, 256, 128, 4), (1, 128, 256, 8), (9, 512, 128, 4),
+              # head_dim 16 with the fewest key blocks (L = 128: two blocks, no ring refill) and a three-block case
+              (3, 128, 64, 4), (2, 384, 64, 4)]
 
 
 @pytest.mark.parametrize("case", ATTN_CASES, ids=[f"B{b}_L{l}_C{c}_h{h}" for b, l, c, h in ATTN_CASES])
