@@ -9,7 +9,7 @@ import os
 import re
 import sys
 
-CLASS_OF = [("attn_tc5", "attn_tc32"), ("attn_tc", "attn_tc"), ("conv_tc_kernel", "conv_tc"), ("gemm_stream_kernel", "gemm_stream"), ("norm_fused_kernel", "norm_fused"),
+CLASS_OF = [("attn_tc5", "attn_tc32"), ("attn_tc", "attn_tc"), ("conv_tc_kernel", "conv_tc"), ("conv_tcp_kernel", "conv_tc"), ("gemm_stream_kernel", "gemm_stream"), ("norm_fused_kernel", "norm_fused"),
             ("attn_block_kernel", "attn_block"), ("flash_attn_kernel", "flash_attn"), ("attn_wide_kernel", "flash_attn"),
             ("tail_tc_kernel", "tail_conv"), ("tail_mma_kernel", "tail_conv"), ("tail_conv_kernel", "tail_conv"), ("stem_mma_kernel", "stem_conv"),
             ("stem_conv_kernel", "stem_conv"), ("plane_stats_kernel", "plane_stats"), ("temb_project_kernel", "temb_project"),
