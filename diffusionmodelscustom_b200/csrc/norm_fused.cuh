@@ -133,59 +133,74 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
     __syncthreads();
     // no CTA may exit (and release its shared memory) while a peer can still read its partials
     cluster_arrive_release();
-    // ---- apply from shared memory
-    for (int i = threadIdx.x, k = 0; i < nrows * 8; i += 256, ++k) {
-        const int r = i >> 3, c8 = (i & 7) * 8;
-        const uint4 xv = *reinterpret_cast<const uint4*>(tile + (size_t)r * 128 + c8 * 2);
-        const size_t e = base + (size_t)(r0 + r) * row_pitch + c8;
-        float f[8];
-        float2 t;
-        t = unpack_h2(xv.x); f[0] = t.x; f[1] = t.y;
-        t = unpack_h2(xv.y); f[2] = t.x; f[3] = t.y;
-        t = unpack_h2(xv.z); f[4] = t.x; f[5] = t.y;
-        t = unpack_h2(xv.w); f[6] = t.x; f[7] = t.y;
-        int ch;                                                 // channel of f[0] in the tensor
-        if (MODE == 0) {
-            ch = grp * 64 + c8;
+    // ---- apply from shared memory, four items per thread at a time: the skip / residual vectors of all four are requested
+    // before any arithmetic (one dependent global load per iteration kept a single 16-byte load in flight per thread:
+    // ncu long-scoreboard stall 7.0, 2.9 TB/s)
+    const int nitems = nrows * 8;
+    for (int i0 = threadIdx.x, k0 = 0; i0 < nitems; i0 += 4 * 256, k0 += 4) {
+        uint4 av[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (f[j] - s_mean[c8 + j]) * s_rstd[c8 + j];
-        } else {
-            ch = (int)(((size_t)(r0 + r) * 64 + c8) % p.C);
-            const float mean = s_mean[0], rstd = s_rstd[0];
-            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + ch + 4));
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + ch + 4));
-            const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
-        }
-        if (p.add) {
-            uint4 av;
-            if (pre_add) av = (k == 0) ? addv[0] : (k == 1) ? addv[1] : (k == 2) ? addv[2] : addv[3];
-            else av = *reinterpret_cast<const uint4*>(p.add + e);
-            t = unpack_h2(av.x); f[0] += t.x; f[1] += t.y;
-            t = unpack_h2(av.y); f[2] += t.x; f[3] += t.y;
-            t = unpack_h2(av.z); f[4] += t.x; f[5] += t.y;
-            t = unpack_h2(av.w); f[6] += t.x; f[7] += t.y;
-        }
-        if (MODE == 1 && p.act == 2) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (p.vec) {
-            if (MODE == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += s_vec[c8 + j];
-            } else {
-                const float* vp = p.vec + (size_t)b * p.vec_stride + ch;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] += vp[j];
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256;
+            av[u] = make_uint4(0, 0, 0, 0);
+            if (p.add && i < nitems) {
+                if (pre_add) av[u] = addv[u];                    // nitems <= 4 * 256: k0 == 0
+                else av[u] = *reinterpret_cast<const uint4*>(p.add + base + (size_t)(r0 + (i >> 3)) * row_pitch + (i & 7) * 8);
             }
         }
-        uint4 o;
-        o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
-        o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-        *reinterpret_cast<uint4*>(p.y + e) = o;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256;
+            if (i >= nitems) break;
+            const int r = i >> 3, c8 = (i & 7) * 8;
+            const uint4 xv = *reinterpret_cast<const uint4*>(tile + (size_t)r * 128 + c8 * 2);
+            const size_t e = base + (size_t)(r0 + r) * row_pitch + c8;
+            float f[8];
+            float2 t;
+            t = unpack_h2(xv.x); f[0] = t.x; f[1] = t.y;
+            t = unpack_h2(xv.y); f[2] = t.x; f[3] = t.y;
+            t = unpack_h2(xv.z); f[4] = t.x; f[5] = t.y;
+            t = unpack_h2(xv.w); f[6] = t.x; f[7] = t.y;
+            int ch;                                                 // channel of f[0] in the tensor
+            if (MODE == 0) {
+                ch = grp * 64 + c8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = (f[j] - s_mean[c8 + j]) * s_rstd[c8 + j];
+            } else {
+                ch = (int)(((size_t)(r0 + r) * 64 + c8) % p.C);
+                const float mean = s_mean[0], rstd = s_rstd[0];
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + ch)), g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + ch + 4));
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta + ch)), b1 = __ldg(reinterpret_cast<const float4*>(p.beta + ch + 4));
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * gg[j] + bb[j];
+            }
+            if (p.add) {
+                t = unpack_h2(av[u].x); f[0] += t.x; f[1] += t.y;
+                t = unpack_h2(av[u].y); f[2] += t.x; f[3] += t.y;
+                t = unpack_h2(av[u].z); f[4] += t.x; f[5] += t.y;
+                t = unpack_h2(av[u].w); f[6] += t.x; f[7] += t.y;
+            }
+            if (MODE == 1 && p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]);
+            }
+            if (p.vec) {
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += s_vec[c8 + j];
+                } else {
+                    const float* vp = p.vec + (size_t)b * p.vec_stride + ch;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += vp[j];
+                }
+            }
+            uint4 o;
+            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
+            o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(p.y + e) = o;
+        }
     }
     cluster_wait_acquire();
 }
