@@ -1611,6 +1611,42 @@ int b2d_op_instnorm(const void* x, const void* skip, const float* vec, int32_t v
     return 0;
 }
 
+int b2d_op_final_layer(const void* x, const float* w, const float* bias, float* out, int32_t B, int32_t H, int32_t W,
+                       int32_t use_mma_sync, void* stream) {
+    cudaStream_t st = as_stream(stream);
+    B2D_CHECK(x && w && bias && out && B >= 1 && H >= 1 && W >= 1, "bad argument");
+    const int HW = H * W, C = 64;
+    const int nslab = (HW + 255) / 256;
+    float* ws = nullptr;
+    const size_t n_stats = (size_t)B * C * 2, n_part = (size_t)B * nslab * 128, n_cnt = (size_t)B;
+    B2D_CUDA(cudaMalloc(&ws, (n_stats + n_part + n_cnt) * 4));
+    float* stats = ws;
+    float* partial = ws + n_stats;
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ws + n_stats + n_part);
+    cudaMemsetAsync(counters, 0, n_cnt * 4, st);
+    int rc = 0;
+    do {
+        cudaError_t e = launch_k(plane_stats_kernel, dim3(nslab, 1, B), dim3(256), 0, st, (const f16*)x, partial, counters, stats, HW, C, 256);
+        if (e != cudaSuccess) { rc = fail(-2, cudaGetErrorString(e)); break; }
+        if (!use_mma_sync && tail_tc_supported(H, W, 1)) {
+            if ((rc = tail_tc_init_attrs())) break;
+            TailTcPlan pl;
+            if ((rc = tail_tc_plan_build(pl, (const f16*)x, B, H, W))) break;
+            rc = tail_tc_launch(pl, stats, w, bias, out, H, W, st);
+        } else {
+            e = cudaFuncSetAttribute(tail_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TAILM_SMEM);
+            if (e == cudaSuccess)
+                e = launch_k(tail_mma_kernel, dim3((W + 31) / 32, (H + 7) / 8, B), dim3(256), TAILM_SMEM, st, (const f16*)x, stats, w, bias, out, H, W, 1);
+            if (e != cudaSuccess) rc = fail(-2, cudaGetErrorString(e));
+        }
+    } while (0);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaFree(ws);
+    if (rc) return rc;
+    B2D_CUDA(e2);
+    return 0;
+}
+
 int b2d_op_posterior_update(float* x, const float* eps, const float* z, const float* betas, const float* alphas,
                             const float* alpha_hat, int32_t i, int32_t B, int64_t per_sample, uint64_t seed,
                             uint64_t sample_offset, float noise_scale, void* stream) {

@@ -208,6 +208,11 @@ int b2d_op_attn_block_out(const void* x_f16, const void* w_folded_f16, const flo
                           int32_t final_act, void* stream);
 int b2d_op_instnorm(const void* x_f16, const void* skip_f16, const float* vec, int32_t vec_stride, void* y_f16,
                     float* stats_ws, int32_t B, int32_t HW, int32_t C, void* stream);
+/* Decoder.final_layer without its ConvTranspose (modules_DANRA_conditional.py:503-509): InstanceNorm2d(64) -> Conv2d(64 -> 1, 3x3,
+ * pad 1) + bias on x [B,H,W,64] f16 -> out [B,1,H,W] fp32.  w: conv weight fp32, K-major [tap * 64 + c] (tap = 3*ky + kx).
+ * use_mma_sync != 0 selects the legacy tail_mma_kernel instead of the tcgen05 tail (A/B and the c_out > 1 path). */
+int b2d_op_final_layer(const void* x_f16, const float* w_kmajor, const float* bias, float* out, int32_t B, int32_t H, int32_t W,
+                       int32_t use_mma_sync, void* stream);
 int b2d_op_posterior_update(float* x, const float* eps, const float* z_or_null, const float* betas, const float* alphas,
                             const float* alpha_hat, int32_t i, int32_t B, int64_t per_sample, uint64_t seed,
                             uint64_t sample_offset, float noise_scale, void* stream);

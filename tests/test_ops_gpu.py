@@ -305,6 +305,31 @@ def test_instance_norm_with_skip_and_vector(shape):
     assert G.rel_l2(y.float().cpu(), ref) < TOL
 
 
+# Decoder.final_layer after its ConvTranspose: InstanceNorm2d -> Conv3x3(64 -> 1) (modules_DANRA_conditional.py:503-509).  The tcgen05
+# kernel (taps as the N dimension + shifted sum) against torch in fp32, and against the mma.sync kernel it replaces; shapes cover one
+# tile per image (16x8 = 128 pixels), several rows per tile (W = 32, 64), one row per tile (W = 128), bands with and without halo
+# tiles above / below, and a non-zero mean (the mean term is dropped for taps outside the image).
+@pytest.mark.parametrize("shape", [(3, 8, 16), (2, 32, 32), (5, 64, 64), (2, 128, 128), (1, 256, 64)])
+def test_final_layer_instance_norm_conv_matches_torch(shape):
+    B, H, W = shape
+    g = torch.Generator().manual_seed(H * 1000 + W)
+    x = _bf(torch.randn(B, H, W, 64, generator=g) * 1.5 + torch.randn(1, 1, 1, 64, generator=g))
+    wt = torch.randn(1, 64, 3, 3, generator=g) * 0.05
+    bias = torch.randn(1, generator=g)
+    xn = F.instance_norm(x.permute(0, 3, 1, 2), eps=1e-5)
+    ref = F.conv2d(xn, wt, bias, padding=1)
+    wk = wt[0].permute(1, 2, 0).reshape(-1).contiguous()                # [tap * 64 + c]
+    xd, wd, bd = x.to(torch.float16).cuda().contiguous(), wk.cuda(), bias.cuda()
+    outs = []
+    for legacy in (0, 1):
+        out = torch.full((B, 1, H, W), float("nan"), dtype=torch.float32, device="cuda")
+        N.check(N.lib().b2d_op_final_layer(xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), B, H, W, legacy, G.stream()))
+        torch.cuda.synchronize()
+        assert G.rel_l2(out.cpu(), ref) < TOL, legacy
+        outs.append(out)
+    assert G.rel_l2(outs[0].cpu(), outs[1].cpu()) < 1e-3
+
+
 def test_posterior_update_bit_exact_with_host_noise():
     """Same op order as diffusion_DANRA_conditional.py:155-157, no FMA contraction => identical bits."""
     from oracle import ddpm_oracle as O
