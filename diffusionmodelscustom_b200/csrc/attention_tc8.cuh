@@ -27,7 +27,19 @@ constexpr int AT8_EQ_BYTES = ATC_BLK * ATC_D * 2;             // 4 KB
 constexpr int AT8_EK_BYTES = (ATC_BN / 2) * ATC_D * 2;        // 1 KB
 constexpr int AT8_SMEM = 1024 + ATC_TILE_BYTES + ATC_KV_BYTES * 3 * ATC_STAGES + AT8_EQ_BYTES + AT8_EK_BYTES + 256;
 
-constexpr float AT8_OFF_SFU = 7.0f, AT8_OFF_POLY = 22.0f;     // per-column constants added by the tensor core (log2 units)
+// per-column constants added by the tensor core (log2 units): P is stored as p * 2^7 (the factor cancels in O / l; 2^8 * 2^7 still
+// fits fp16), SFU columns receive x + 7, polynomial columns x + 22 (relu clamp = flush below 2^-22).
+// Accuracy trade-off, measured with tools/attn_stress.py (200 random cases, rel-L2 of the attention output against fp64):
+//   * the polynomial path rounds x + OFF_POLY to fp16: in [16, 32) the ulp is 2^-6, i.e. +-0.54 % (0.31 % rms) on every P of a
+//     polynomial column — worst case 2.7e-3 on near-uniform attention (an average of many keys: nothing averages the noise against
+//     the signal).  OFF_POLY = 15 / OFF_SFU = 0 halves that for x <= 1 (1.4e-3) but flushes at 2^-15, and a peaked row over a broad
+//     floor of 4096 keys then loses up to a few per cent of its mass in the polynomial columns (3.3e-3 in the stress set, the same
+//     case where attn_tc3 — which flushed at 2^-15 too — shows 3.5e-3); a clamp by HMNMX2 instead of relu (offset 0: ulp 2^-11 near
+//     x = 0) costs one instruction per pair = ~3.5 % of the kernel.
+//   * at model level none of this is visible: eps_hat rel-L2 against the reference goldens is 1.02e-3 mean / 1.84e-3 max with this
+//     kernel, with attn_tc3 and with the fp32-softmax mma.sync kernel alike (tools/eps_error.py) — the attention output is a small
+//     residual contribution next to the fp16 storage of every activation.
+constexpr float AT8_OFF_SFU = 7.0f, AT8_OFF_POLY = 22.0f;
 
 // 2^(x' - 15) for a pair of fp32 arguments x' in (-inf, 30] on the FMA pipe in packed half precision; x' <= 0 flushes to +0 exactly
 __device__ __forceinline__ uint32_t ex2_pair_poly_off(float xa, float xb) {
@@ -90,7 +102,7 @@ __global__ void __launch_bounds__(AT8_THREADS, AT6_CTAS_PER_SM)
     for (int i = threadIdx.x; i < AT8_EQ_BYTES / 16; i += NT) *reinterpret_cast<uint4*>(sEq + i * 16) = make_uint4(0u, 0x00003C00u, 0u, 0u);
     for (int i = threadIdx.x; i < AT8_EK_BYTES / 16; i += NT) {
         const int pair = (i >> 1) >> 1;                                  // S column = E_k row = i >> 1; two columns per fp16 pair
-        const uint32_t half_off = ((pair & 7) < POLY) ? 0x4980u /* 11 */ : 0x4300u /* 3.5 */;
+        const uint32_t half_off = ((pair & 7) < POLY) ? 0x4980u /* OFF_POLY / 2 = 11 */ : 0x4300u /* OFF_SFU / 2 = 3.5 */;
         *reinterpret_cast<uint4*>(sEk + i * 16) = make_uint4(0x38003800u, half_off, 0u, 0u);
     }
     fence_proxy_async();
