@@ -18,8 +18,14 @@
 
 namespace b2d {
 
-constexpr int CONVP_THREADS = 320;
-constexpr int CONVP_EPI_THREADS = 256;
+constexpr int CONVP_EPI_THREADS = 256;                 // per epilogue group
+// EG = 2: TWO epilogue groups of eight warps, group e drains the tiles with (tile counter & 1) == e, i.e. it owns accumulator stage
+// e, with its own staging / residual tiles, bias slice and named barrier.  For BN = 64 the epilogue of a tile (tcgen05.ld ->
+// bias / residual / activation / vector -> pack -> staging -> TMA store, ~600 dependent instructions per thread with two warps per
+// scheduler) takes ~5000 clk against ~2100-2500 clk of shared-memory fill per tile: ncu showed the 64 -> 64 3x3 layers at 27 % tensor
+// pipe with the tile rate set by the epilogue.  Two groups drain two tiles at a time.
+template <int EG>
+__host__ __device__ constexpr int convp_threads() { return 64 + EG * CONVP_EPI_THREADS; }
 
 // SLAB mode (3x3, stride 1, tiles of 16 x 8 pixels inside one image): the A operand of the three taps of one filter COLUMN is one
 // (8+2)-row x 16-pixel slab, loaded once; tap r is the same shared-memory tile 16 rows (= 2 KB, a multiple of the 1 KB swizzle
@@ -33,13 +39,13 @@ template <int BN, bool SLAB>
 __host__ __device__ constexpr int convp_stage_bytes() {
     return SLAB ? CONVP_SLAB_A_BYTES + 3 * BN * 128 : conv_stage_bytes<BN>();
 }
-template <int BN, int STAGES, bool SLAB>
+template <int BN, int STAGES, bool SLAB, int EG>
 __host__ __device__ constexpr int convp_smem_bytes() {
-    return STAGES * convp_stage_bytes<BN, SLAB>() + 2 * (BN / 64) * CONV_A_BYTES /* staging + residual */ + 1024 /*align*/ + 512 /*barriers*/;
+    return STAGES * convp_stage_bytes<BN, SLAB>() + EG * 2 * (BN / 64) * CONV_A_BYTES /* staging + residual */ + 1024 /*align*/ + 512 /*barriers*/;
 }
 
-template <int BN, int STAGES, bool SLAB>
-__global__ void __launch_bounds__(CONVP_THREADS, 1)
+template <int BN, int STAGES, bool SLAB, int EG>
+__global__ void __launch_bounds__(convp_threads<EG>(), 1)
     conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvParams p,
                     const int mtiles, const int ntiles) {
@@ -50,18 +56,18 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
     constexpr int B_BYTES = SLAB ? 3 * BN * 128 : BN * 128;
     uint8_t* sA = smem;                                             // STAGES x A_BYTES
     uint8_t* sB = sA + STAGES * A_BYTES;                            // STAGES x B_BYTES
-    uint8_t* sO = sB + STAGES * B_BYTES;                            // BN/64 staging tiles (128 rows x 128 B, 128B swizzle)
-    uint8_t* sR = sO + (BN / 64) * CONV_A_BYTES;                    // BN/64 residual tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (BN / 64) * CONV_A_BYTES);
+    uint8_t* sO = sB + STAGES * B_BYTES;                            // EG x BN/64 staging tiles (128 rows x 128 B, 128B swizzle)
+    uint8_t* sR = sO + EG * (BN / 64) * CONV_A_BYTES;               // EG x BN/64 residual tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + EG * (BN / 64) * CONV_A_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* acc_full = bars + 2 * STAGES;        // [2]
     uint64_t* acc_empty = bars + 2 * STAGES + 2;   // [2]  eight arrivals (epilogue warps)
-    uint64_t* res_full = bars + 2 * STAGES + 4;
-    uint64_t* res_empty = bars + 2 * STAGES + 5;   // eight arrivals
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
-    __shared__ __align__(16) float s_bias[2][BN];
-    __shared__ float s_red[8][2];
+    uint64_t* res_full = bars + 2 * STAGES + 4;    // [EG]
+    uint64_t* res_empty = bars + 2 * STAGES + 6;   // [EG] eight arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+    __shared__ __align__(16) float s_bias[EG][BN];
+    __shared__ float s_red[EG][8][2];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -83,8 +89,10 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                 mbar_init(&acc_full[i], 1);
                 mbar_init(&acc_empty[i], 8);
             }
-            mbar_init(res_full, 1);
-            mbar_init(res_empty, 8);
+            for (int i = 0; i < EG; ++i) {
+                mbar_init(&res_full[i], 1);
+                mbar_init(&res_empty[i], 8);
+            }
             fence_mbar_init();
         }
         __syncwarp();
@@ -169,17 +177,19 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
             }
             }
             if (p.residual != nullptr) {
-                mbar_wait(res_empty, (it & 1) ^ 1);            // the epilogue has read the previous tile's residual
+                const int e = (EG == 2) ? (it & 1) : 0;        // the group that will drain this tile
+                const int ei = (EG == 2) ? (it >> 1) : it;     // ... and how many tiles it has drained before
+                mbar_wait(&res_empty[e], (ei & 1) ^ 1);        // that group has read its previous tile's residual
                 if (elect_one()) {
-                    mbar_arrive_expect_tx(res_full, (BN / 64) * CONV_A_BYTES);
+                    mbar_arrive_expect_tx(&res_full[e], (BN / 64) * CONV_A_BYTES);
                     for (int jb = 0; jb < BN / 64; ++jb) {
-                        void* dst = sR + jb * CONV_A_BYTES;
+                        void* dst = sR + (e * (BN / 64) + jb) * CONV_A_BYTES;
                         if (p.convt) {
                             const int ab = (nblk * BN) / p.CoutT;
                             const int cb0 = (nblk * BN) - ab * p.CoutT + jb * 64;
-                            tma_load_5d(dst, &tmR, res_full, (ab & 1) * p.CoutT + cb0, w0, ab >> 1, h0, n0);
+                            tma_load_5d(dst, &tmR, &res_full[e], (ab & 1) * p.CoutT + cb0, w0, ab >> 1, h0, n0);
                         } else {
-                            tma_load_4d(dst, &tmR, res_full, nblk * BN + jb * 64, w0, h0, n0);
+                            tma_load_4d(dst, &tmR, &res_full[e], nblk * BN + jb * 64, w0, h0, n0);
                         }
                     }
                 }
@@ -229,10 +239,14 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
     } else {
         // ===================== epilogue warps =====================
         const int q = warp & 3;
-        const int g = (warp - 2) >> 2;                          // 0 / 1
+        const int eg = (warp - 2) >> 3;                         // epilogue group (0 when EG == 1)
+        const int g = ((warp - 2) >> 2) & 1;                    // 0 / 1 within the group
         const int row = q * 32 + lane;
         const int sw = row & 7;
-        const int et = threadIdx.x - 64;                        // 0..255
+        const int et = threadIdx.x - 64 - eg * CONVP_EPI_THREADS;   // 0..255 within the group
+        const int bar_id = 1 + eg;
+        uint8_t* const sOg = sO + eg * (BN / 64) * CONV_A_BYTES;
+        uint8_t* const sRg = sR + eg * (BN / 64) * CONV_A_BYTES;
         const int lw = row % p.TW;
         const int lh = (row / p.TW) % p.TH;
         const int ln = row / (p.TW * p.TH);
@@ -241,7 +255,9 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
         int bias_nblk = -1;
         int it = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+            if (EG == 2 && (it & 1) != eg) continue;            // the other group's tile
             const int acc = it & 1;
+            const int gi = (EG == 2) ? (it >> 1) : it;          // tiles this group has drained before
             const int mt = t / ntiles, nblk = t - mt * ntiles;
             const int tw = mt % p.tiles_w, th = (mt / p.tiles_w) % p.tiles_h, tb = mt / per_img;
             const int w0 = tw * p.TW, h0 = th * p.TH, n0 = tb * p.TN;
@@ -256,9 +272,9 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                 cbase = nblk * BN;
             }
             // the bias slice only changes with the N block (never, for the many single-N-block layers): no global load per tile
-            float* bias_s = s_bias[0];
+            float* bias_s = s_bias[eg];
             if (nblk != bias_nblk) {
-                named_bar_sync(1, CONVP_EPI_THREADS);           // every reader of the previous slice is done
+                named_bar_sync(bar_id, CONVP_EPI_THREADS);      // every reader of the previous slice is done
                 if (et < BN) bias_s[et] = p.bias ? __ldg(p.bias + cbase + et) : 0.f;
                 bias_nblk = nblk;
             }
@@ -275,11 +291,11 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
             }
             // the stores of the previous tile must have read the staging tiles before they are overwritten
             if (et < BN / 64) tma_store_wait_read();            // bulk groups are per thread: the threads that issued the stores wait
-            named_bar_sync(1, CONVP_EPI_THREADS);
+            named_bar_sync(bar_id, CONVP_EPI_THREADS);
 
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
-            if (p.residual != nullptr) mbar_wait(res_full, it & 1);
+            if (p.residual != nullptr) mbar_wait(&res_full[eg], gi & 1);
             float gs1 = 0.f, gs2 = 0.f;
             constexpr int NCH = BN / 64;                        // 32-column chunks per warp: 1 (BN=64) or 2 (BN=128)
 #pragma unroll
@@ -290,7 +306,7 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                 uint32_t v[32];
                 tmem_ld32(tmem_base + lane_off + (uint32_t)(acc * BN + ch * 32), v);
                 tmem_ld_wait();
-                uint4* srow = reinterpret_cast<uint4*>(sO + jb * CONV_A_BYTES + row * 128);
+                uint4* srow = reinterpret_cast<uint4*>(sOg + jb * CONV_A_BYTES + row * 128);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -301,7 +317,7 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                     f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
                 }
                 if (p.residual) {
-                    const uint4* rrow = reinterpret_cast<const uint4*>(sR + jb * CONV_A_BYTES + row * 128);
+                    const uint4* rrow = reinterpret_cast<const uint4*>(sRg + jb * CONV_A_BYTES + row * 128);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const uint4 r4 = rrow[(half * 4 + j) ^ sw];
@@ -345,22 +361,22 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&acc_empty[acc]);
-                if (p.residual != nullptr) mbar_arrive(res_empty);
+                if (p.residual != nullptr) mbar_arrive(&res_empty[eg]);
             }
             if (p.gn_partial != nullptr) {
                 gs1 = warp_sum(gs1);
                 gs2 = warp_sum(gs2);
                 if (lane == 0) {
-                    s_red[warp - 2][0] = gs1;
-                    s_red[warp - 2][1] = gs2;
+                    s_red[eg][(warp - 2) & 7][0] = gs1;
+                    s_red[eg][(warp - 2) & 7][1] = gs2;
                 }
             }
             fence_proxy_async();                                // generic-proxy smem writes -> visible to the TMA engine
-            named_bar_sync(1, CONVP_EPI_THREADS);
+            named_bar_sync(bar_id, CONVP_EPI_THREADS);
             if (et < BN / 64) {                                 // one thread per 64-channel block issues its store
                 const int jb = et;
-                if (p.convt) tma_store_5d(&tmO, sO + jb * CONV_A_BYTES, (ab & 1) * p.CoutT + cbase + jb * 64, w0, ab >> 1, h0, n0);
-                else tma_store_4d(&tmO, sO + jb * CONV_A_BYTES, cbase + jb * 64, w0, h0, n0);
+                if (p.convt) tma_store_5d(&tmO, sOg + jb * CONV_A_BYTES, (ab & 1) * p.CoutT + cbase + jb * 64, w0, ab >> 1, h0, n0);
+                else tma_store_4d(&tmO, sOg + jb * CONV_A_BYTES, cbase + jb * 64, w0, h0, n0);
                 tma_store_commit();
             }
             if (p.gn_partial != nullptr) {                      // fixed-order combination: deterministic
@@ -368,16 +384,16 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
                     if (g == 0 && lane == 0) {
                         const size_t o = (((size_t)nblk * mtiles + mt) * 4 + q) * 2;
                         // same association as the one-tile kernel: a quarter's 64 (or 128) columns are summed per row first
-                        p.gn_partial[o] = s_red[q][0] + s_red[4 + q][0];
-                        p.gn_partial[o + 1] = s_red[q][1] + s_red[4 + q][1];
+                        p.gn_partial[o] = s_red[eg][q][0] + s_red[eg][4 + q][0];
+                        p.gn_partial[o + 1] = s_red[eg][q][1] + s_red[eg][4 + q][1];
                     }
                 } else if (et == 64) {
                     const size_t o = ((size_t)nblk * mtiles + mt) * 2;
                     float a = 0.f, b = 0.f;
 #pragma unroll
                     for (int w = 0; w < 8; ++w) {
-                        a += s_red[w][0];
-                        b += s_red[w][1];
+                        a += s_red[eg][w][0];
+                        b += s_red[eg][w][1];
                     }
                     p.gn_partial[o] = a;
                     p.gn_partial[o + 1] = b;
@@ -395,19 +411,26 @@ __global__ void __launch_bounds__(CONVP_THREADS, 1)
     }
 }
 
-template <int BN, int STAGES, bool SLAB>
+template <int BN, int STAGES, bool SLAB, int EG>
 inline int conv_tcp_set_attr() {
-    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  convp_smem_bytes<BN, STAGES, SLAB>()));
-    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    static_assert(convp_smem_bytes<BN, STAGES, SLAB, EG>() <= 227 * 1024, "shared memory budget");
+    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  convp_smem_bytes<BN, STAGES, SLAB, EG>()));
+    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB, EG>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
     return 0;
 }
+inline bool conv_tcp_one_group() {
+    static const bool v = getenv("B2D_CONV_ONE_EPI_GROUP") != nullptr;      // A/B: one epilogue group for BN = 64 too
+    return v;
+}
 inline int conv_tcp_init_attrs() {
-    B2D_TRY((conv_tcp_set_attr<64, 8, false>()));
-    B2D_TRY((conv_tcp_set_attr<128, 5, false>()));
-    B2D_TRY((conv_tcp_set_attr<64, 4, true>()));
-    B2D_TRY((conv_tcp_set_attr<128, 2, true>()));
+    B2D_TRY((conv_tcp_set_attr<64, 8, false, 1>()));
+    B2D_TRY((conv_tcp_set_attr<64, 6, false, 2>()));
+    B2D_TRY((conv_tcp_set_attr<128, 5, false, 1>()));
+    B2D_TRY((conv_tcp_set_attr<64, 4, true, 1>()));
+    B2D_TRY((conv_tcp_set_attr<64, 3, true, 2>()));
+    B2D_TRY((conv_tcp_set_attr<128, 2, true, 1>()));
     return 0;
 }
 
@@ -421,21 +444,30 @@ inline bool conv_tcp_eligible(const ConvPlan& pl, int num_sms, int min_tiles_per
     return tiles >= min_tiles_per_sm * num_sms;
 }
 
-template <int BN, int STAGES, bool SLAB>
+template <int BN, int STAGES, bool SLAB, int EG>
 inline int conv_tcp_launch_t(const ConvPlan& pl, int num_sms, cudaStream_t st) {
     const int mtiles = (int)pl.grid.x, ntiles = (int)pl.grid.y;
     const int tiles = mtiles * ntiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    B2D_CUDA(launch_k(conv_tcp_kernel<BN, STAGES, SLAB>, dim3(grid), dim3(CONVP_THREADS), (size_t)convp_smem_bytes<BN, STAGES, SLAB>(), st,
-                      pl.tmA, pl.tmB, pl.tmO, pl.tmR, pl.p, mtiles, ntiles));
+    B2D_CUDA(launch_k(conv_tcp_kernel<BN, STAGES, SLAB, EG>, dim3(grid), dim3(convp_threads<EG>()),
+                      (size_t)convp_smem_bytes<BN, STAGES, SLAB, EG>(), st, pl.tmA, pl.tmB, pl.tmO, pl.tmR, pl.p, mtiles, ntiles));
     return 0;
 }
 inline int conv_launch_tcp(const ConvPlan& pl, int num_sms, cudaStream_t st) {
     B2D_CHECK(pl.tc_ready && pl.p.splits == 1, "persistent conv needs an un-split plan");
-    if (pl.slab) return pl.bn == 64 ? conv_tcp_launch_t<64, 4, true>(pl, num_sms, st) : conv_tcp_launch_t<128, 2, true>(pl, num_sms, st);
+    // BN = 64: two epilogue groups where the tile rate is set by the epilogue — an epilogue with activation / residual / vector
+    // (measured: 64 -> 64 3x3 + ReLU 51 -> 33 us at B=256; the plain-bias epilogue of the decoder convs is 5 % FASTER with one group
+    // and the deeper ring) — and the K loop is not so deep that the ring depth matters more
+    const int kblocks = pl.p.R * pl.p.S * (pl.p.Cin >> 6);
+    const bool heavy = pl.p.act != 0 || pl.p.residual != nullptr || pl.p.post_add != nullptr;
+    const bool two = pl.bn == 64 && !conv_tcp_one_group() && kblocks <= 36 && heavy;
+    if (pl.slab)
+        return pl.bn == 64 ? (two ? conv_tcp_launch_t<64, 3, true, 2>(pl, num_sms, st) : conv_tcp_launch_t<64, 4, true, 1>(pl, num_sms, st))
+                           : conv_tcp_launch_t<128, 2, true, 1>(pl, num_sms, st);
     // deepest rings that fit next to the staging / residual tiles (224 KB): the deep-K layers are paced by the bytes a single
     // SM keeps in flight
-    return pl.bn == 64 ? conv_tcp_launch_t<64, 8, false>(pl, num_sms, st) : conv_tcp_launch_t<128, 5, false>(pl, num_sms, st);
+    return pl.bn == 64 ? (two ? conv_tcp_launch_t<64, 6, false, 2>(pl, num_sms, st) : conv_tcp_launch_t<64, 8, false, 1>(pl, num_sms, st))
+                       : conv_tcp_launch_t<128, 5, false, 1>(pl, num_sms, st);
 }
 
 }  // namespace b2d
