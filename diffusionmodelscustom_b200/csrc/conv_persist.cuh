@@ -39,12 +39,14 @@ template <int BN, bool SLAB>
 __host__ __device__ constexpr int convp_stage_bytes() {
     return SLAB ? CONVP_SLAB_A_BYTES + 3 * BN * 128 : conv_stage_bytes<BN>();
 }
-template <int BN, int STAGES, bool SLAB, int EG>
+// RES = false: a build without the residual tiles (layers without a residual operand): their shared memory goes to the ring
+template <int BN, int STAGES, bool SLAB, int EG, bool RES>
 __host__ __device__ constexpr int convp_smem_bytes() {
-    return STAGES * convp_stage_bytes<BN, SLAB>() + EG * 2 * (BN / 64) * CONV_A_BYTES /* staging + residual */ + 1024 /*align*/ + 512 /*barriers*/;
+    return STAGES * convp_stage_bytes<BN, SLAB>() + EG * (RES ? 2 : 1) * (BN / 64) * CONV_A_BYTES /* staging + residual */ + 1024 /*align*/ +
+           512 /*barriers*/;
 }
 
-template <int BN, int STAGES, bool SLAB, int EG>
+template <int BN, int STAGES, bool SLAB, int EG, bool RES>
 __global__ void __launch_bounds__(convp_threads<EG>(), 1)
     conv_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR, const ConvParams p,
@@ -57,8 +59,8 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
     uint8_t* sA = smem;                                             // STAGES x A_BYTES
     uint8_t* sB = sA + STAGES * A_BYTES;                            // STAGES x B_BYTES
     uint8_t* sO = sB + STAGES * B_BYTES;                            // EG x BN/64 staging tiles (128 rows x 128 B, 128B swizzle)
-    uint8_t* sR = sO + EG * (BN / 64) * CONV_A_BYTES;               // EG x BN/64 residual tiles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + EG * (BN / 64) * CONV_A_BYTES);
+    uint8_t* sR = sO + EG * (BN / 64) * CONV_A_BYTES;               // EG x BN/64 residual tiles (RES builds only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sR + (RES ? EG * (BN / 64) * CONV_A_BYTES : 0));
     uint64_t* full = bars;
     uint64_t* empty = bars + STAGES;
     uint64_t* acc_full = bars + 2 * STAGES;        // [2]
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
                 }
             }
             }
-            if (p.residual != nullptr) {
+            if (RES && p.residual != nullptr) {
                 const int e = (EG == 2) ? (it & 1) : 0;        // the group that will drain this tile
                 const int ei = (EG == 2) ? (it >> 1) : it;     // ... and how many tiles it has drained before
                 mbar_wait(&res_empty[e], (ei & 1) ^ 1);        // that group has read its previous tile's residual
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
 
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
-            if (p.residual != nullptr) mbar_wait(&res_full[eg], gi & 1);
+            if (RES && p.residual != nullptr) mbar_wait(&res_full[eg], gi & 1);
             float gs1 = 0.f, gs2 = 0.f;
             constexpr int NCH = BN / 64;                        // 32-column chunks per warp: 1 (BN=64) or 2 (BN=128)
 #pragma unroll
@@ -316,7 +318,7 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
                     f[j + 2] = __uint_as_float(v[j + 2]) + b4.z;
                     f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
                 }
-                if (p.residual) {
+                if (RES && p.residual) {
                     const uint4* rrow = reinterpret_cast<const uint4*>(sRg + jb * CONV_A_BYTES + row * 128);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&acc_empty[acc]);
-                if (p.residual != nullptr) mbar_arrive(&res_empty[eg]);
+                if (RES && p.residual != nullptr) mbar_arrive(&res_empty[eg]);
             }
             if (p.gn_partial != nullptr) {
                 gs1 = warp_sum(gs1);
@@ -411,12 +413,12 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
     }
 }
 
-template <int BN, int STAGES, bool SLAB, int EG>
+template <int BN, int STAGES, bool SLAB, int EG, bool RES>
 inline int conv_tcp_set_attr() {
-    static_assert(convp_smem_bytes<BN, STAGES, SLAB, EG>() <= 227 * 1024, "shared memory budget");
-    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB, EG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  convp_smem_bytes<BN, STAGES, SLAB, EG>()));
-    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB, EG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    static_assert(convp_smem_bytes<BN, STAGES, SLAB, EG, RES>() <= 227 * 1024, "shared memory budget");
+    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB, EG, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  convp_smem_bytes<BN, STAGES, SLAB, EG, RES>()));
+    B2D_CUDA(cudaFuncSetAttribute(conv_tcp_kernel<BN, STAGES, SLAB, EG, RES>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
     return 0;
 }
@@ -425,12 +427,14 @@ inline bool conv_tcp_one_group() {
     return v;
 }
 inline int conv_tcp_init_attrs() {
-    B2D_TRY((conv_tcp_set_attr<64, 8, false, 1>()));
-    B2D_TRY((conv_tcp_set_attr<64, 6, false, 2>()));
-    B2D_TRY((conv_tcp_set_attr<128, 5, false, 1>()));
-    B2D_TRY((conv_tcp_set_attr<64, 4, true, 1>()));
-    B2D_TRY((conv_tcp_set_attr<64, 3, true, 2>()));
-    B2D_TRY((conv_tcp_set_attr<128, 2, true, 1>()));
+    B2D_TRY((conv_tcp_set_attr<64, 8, false, 1, true>()));
+    B2D_TRY((conv_tcp_set_attr<64, 6, false, 2, true>()));
+    B2D_TRY((conv_tcp_set_attr<64, 7, false, 2, false>()));
+    B2D_TRY((conv_tcp_set_attr<128, 5, false, 1, true>()));
+    B2D_TRY((conv_tcp_set_attr<64, 4, true, 1, true>()));
+    B2D_TRY((conv_tcp_set_attr<64, 3, true, 2, true>()));
+    B2D_TRY((conv_tcp_set_attr<64, 4, true, 2, false>()));
+    B2D_TRY((conv_tcp_set_attr<128, 2, true, 1, true>()));
     return 0;
 }
 
@@ -444,30 +448,33 @@ inline bool conv_tcp_eligible(const ConvPlan& pl, int num_sms, int min_tiles_per
     return tiles >= min_tiles_per_sm * num_sms;
 }
 
-template <int BN, int STAGES, bool SLAB, int EG>
+template <int BN, int STAGES, bool SLAB, int EG, bool RES>
 inline int conv_tcp_launch_t(const ConvPlan& pl, int num_sms, cudaStream_t st) {
     const int mtiles = (int)pl.grid.x, ntiles = (int)pl.grid.y;
     const int tiles = mtiles * ntiles;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    B2D_CUDA(launch_k(conv_tcp_kernel<BN, STAGES, SLAB, EG>, dim3(grid), dim3(convp_threads<EG>()),
-                      (size_t)convp_smem_bytes<BN, STAGES, SLAB, EG>(), st, pl.tmA, pl.tmB, pl.tmO, pl.tmR, pl.p, mtiles, ntiles));
+    B2D_CUDA(launch_k(conv_tcp_kernel<BN, STAGES, SLAB, EG, RES>, dim3(grid), dim3(convp_threads<EG>()),
+                      (size_t)convp_smem_bytes<BN, STAGES, SLAB, EG, RES>(), st, pl.tmA, pl.tmB, pl.tmO, pl.tmR, pl.p, mtiles, ntiles));
     return 0;
 }
 inline int conv_launch_tcp(const ConvPlan& pl, int num_sms, cudaStream_t st) {
     B2D_CHECK(pl.tc_ready && pl.p.splits == 1, "persistent conv needs an un-split plan");
-    // BN = 64: two epilogue groups where the tile rate is set by the epilogue — an epilogue with activation / residual / vector
-    // (measured: 64 -> 64 3x3 + ReLU 51 -> 33 us at B=256; the plain-bias epilogue of the decoder convs is 5 % FASTER with one group
-    // and the deeper ring) — and the K loop is not so deep that the ring depth matters more
+    // BN = 64: two epilogue groups — the tile rate of these layers is set by the epilogue (64 -> 64 3x3 + ReLU: 51 -> 33 us at
+    // B=256) — unless the K loop is so deep that the ring depth matters more.  Layers without a residual operand use the builds
+    // without residual tiles, which keep the ring depth of the one-group kernel next to the second group's staging tile.
     const int kblocks = pl.p.R * pl.p.S * (pl.p.Cin >> 6);
-    const bool heavy = pl.p.act != 0 || pl.p.residual != nullptr || pl.p.post_add != nullptr;
-    const bool two = pl.bn == 64 && !conv_tcp_one_group() && kblocks <= 36 && heavy;
-    if (pl.slab)
-        return pl.bn == 64 ? (two ? conv_tcp_launch_t<64, 3, true, 2>(pl, num_sms, st) : conv_tcp_launch_t<64, 4, true, 1>(pl, num_sms, st))
-                           : conv_tcp_launch_t<128, 2, true, 1>(pl, num_sms, st);
+    const bool res = pl.p.residual != nullptr;
+    const bool two = pl.bn == 64 && !conv_tcp_one_group() && kblocks <= 36;
+    if (pl.slab) {
+        if (pl.bn != 64) return conv_tcp_launch_t<128, 2, true, 1, true>(pl, num_sms, st);
+        if (!two) return conv_tcp_launch_t<64, 4, true, 1, true>(pl, num_sms, st);
+        return res ? conv_tcp_launch_t<64, 3, true, 2, true>(pl, num_sms, st) : conv_tcp_launch_t<64, 4, true, 2, false>(pl, num_sms, st);
+    }
     // deepest rings that fit next to the staging / residual tiles (224 KB): the deep-K layers are paced by the bytes a single
     // SM keeps in flight
-    return pl.bn == 64 ? (two ? conv_tcp_launch_t<64, 6, false, 2>(pl, num_sms, st) : conv_tcp_launch_t<64, 8, false, 1>(pl, num_sms, st))
-                       : conv_tcp_launch_t<128, 5, false, 1>(pl, num_sms, st);
+    if (pl.bn != 64) return conv_tcp_launch_t<128, 5, false, 1, true>(pl, num_sms, st);
+    if (!two) return conv_tcp_launch_t<64, 8, false, 1, true>(pl, num_sms, st);
+    return res ? conv_tcp_launch_t<64, 6, false, 2, true>(pl, num_sms, st) : conv_tcp_launch_t<64, 7, false, 2, false>(pl, num_sms, st);
 }
 
 }  // namespace b2d
