@@ -107,6 +107,20 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     if (fmaxf(fabsf(a), fabsf(b)) > F16_MAX) atomicAdd(&g_sat_count, 1u);
     return r;
 }
+// The same conversion for the GEMM epilogues, where the per-pair test (max, compare, divergent atomic: ~4 extra instructions plus a
+// BSSY/BSYNC pair per two outputs, on a dependent chain that sets the tile rate) is replaced by ONE 3-input maximum per pair into a
+// per-thread running maximum; sat_flush() tests it once per tile.  The counter then counts (thread, tile) pairs with a clamp
+// instead of converted pairs: still zero iff nothing was clamped.
+__device__ __forceinline__ uint32_t pack_h2_acc(float a, float b, float& amax) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
+    return r;
+}
+__device__ __forceinline__ void sat_flush(float& amax) {
+    if (amax > F16_MAX) atomicAdd(&g_sat_count, 1u);
+    amax = 0.f;
+}
 __device__ __forceinline__ uint32_t pack_h2_nosat(float a, float b) {   // inputs known to be in [0, 1]
     f162 v = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);

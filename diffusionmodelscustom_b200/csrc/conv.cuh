@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
             // tile and is read by the same thread first), then one thread issues a TMA store of the whole block.
             const int nr = n < p.B ? n : p.B - 1;                 // out-of-range rows are clipped by the store; keep reads in range
             float gs1 = 0.f, gs2 = 0.f;                           // GroupNorm partial sums of this thread's row
+            float satm = 0.f;                                     // |value| maximum of this thread's conversions (sat_flush below)
             if (p.residual != nullptr) mbar_wait(res_full, 0);
 #pragma unroll 1
             for (int jb = 0; jb < BN / 64; ++jb) {
@@ -395,10 +396,10 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 o;
-                        o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
-                        o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
-                        o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
-                        o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
+                        o.x = pack_h2_acc(f[j * 8 + 0], f[j * 8 + 1], satm);
+                        o.y = pack_h2_acc(f[j * 8 + 2], f[j * 8 + 3], satm);
+                        o.z = pack_h2_acc(f[j * 8 + 4], f[j * 8 + 5], satm);
+                        o.w = pack_h2_acc(f[j * 8 + 6], f[j * 8 + 7], satm);
                         srow[(half * 4 + j) ^ sw] = o;
                     }
                 }
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS)
                     tma_store_commit();
                 }
             }
+            sat_flush(satm);
             if (p.gn_partial != nullptr) {                         // block-reduce the tile's {sum, sumsq} in fixed order
                 gs1 = warp_sum(gs1);
                 gs2 = warp_sum(gs2);

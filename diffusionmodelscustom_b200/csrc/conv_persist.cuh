@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
             mbar_wait(&acc_full[acc], (it >> 1) & 1);
             tc_fence_after();
             if (RES && p.residual != nullptr) mbar_wait(&res_full[eg], gi & 1);
-            float gs1 = 0.f, gs2 = 0.f;
+            float gs1 = 0.f, gs2 = 0.f, satm = 0.f;
             constexpr int NCH = BN / 64;                        // 32-column chunks per warp: 1 (BN=64) or 2 (BN=128)
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -351,13 +351,14 @@ __global__ void __launch_bounds__(convp_threads<EG>(), 1)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     uint4 o;
-                    o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
-                    o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
-                    o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
-                    o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
+                    o.x = pack_h2_acc(f[j * 8 + 0], f[j * 8 + 1], satm);
+                    o.y = pack_h2_acc(f[j * 8 + 2], f[j * 8 + 3], satm);
+                    o.z = pack_h2_acc(f[j * 8 + 4], f[j * 8 + 5], satm);
+                    o.w = pack_h2_acc(f[j * 8 + 6], f[j * 8 + 7], satm);
                     srow[(half * 4 + j) ^ sw] = o;
                 }
             }
+            sat_flush(satm);
             // accumulator stage and residual tile are consumed: hand them back before the store
             tc_fence_before();
             __syncwarp();

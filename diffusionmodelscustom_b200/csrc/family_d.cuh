@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const f16* __restr
     for (int j = 0; j < 8; ++j) vv[j] = (vec && act == 2) ? vec[(size_t)b * vec_stride + c + j] : 0.f;
     const size_t i0 = (size_t)blockIdx.x * (GNA_ITER * 256) + threadIdx.x;
     uint4 xv[GNA_ITER], rv[GNA_ITER];
+    float satm = 0.f;
 #pragma unroll
     for (int it = 0; it < GNA_ITER; ++it) {
         const size_t i = i0 + (size_t)it * 256;
@@ -234,10 +235,11 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const f16* __restr
             for (int j = 0; j < 8; ++j) f[j] = gelu_erf(f[j]) + vv[j];
         }
         uint4 o;
-        o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
-        o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+        o.x = pack_h2_acc(f[0], f[1], satm); o.y = pack_h2_acc(f[2], f[3], satm);
+        o.z = pack_h2_acc(f[4], f[5], satm); o.w = pack_h2_acc(f[6], f[7], satm);
         *reinterpret_cast<uint4*>(y + e) = o;
     }
+    sat_flush(satm);
 }
 
 // ------------------------------------------------------------------------------------------------ MaxPool2d(2), NHWC

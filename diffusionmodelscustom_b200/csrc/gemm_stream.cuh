@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
         }
         named_bar_sync(13, GS_EPI_THREADS);
         int it = 0, blk = 0;                                   // blk: running 64-column block counter
+        float satm = 0.f;                                      // running |value| maximum of this thread's conversions (sat_flush per tile)
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const int m0 = t * 128;
@@ -289,10 +290,10 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         uint4 o;
-                        o.x = pack_h2(f[j * 8 + 0], f[j * 8 + 1]);
-                        o.y = pack_h2(f[j * 8 + 2], f[j * 8 + 3]);
-                        o.z = pack_h2(f[j * 8 + 4], f[j * 8 + 5]);
-                        o.w = pack_h2(f[j * 8 + 6], f[j * 8 + 7]);
+                        o.x = pack_h2_acc(f[j * 8 + 0], f[j * 8 + 1], satm);
+                        o.y = pack_h2_acc(f[j * 8 + 2], f[j * 8 + 3], satm);
+                        o.z = pack_h2_acc(f[j * 8 + 4], f[j * 8 + 5], satm);
+                        o.w = pack_h2_acc(f[j * 8 + 6], f[j * 8 + 7], satm);
                         srow[(half * 4 + j) ^ sw] = o;
                     }
                 }
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(GS_THREADS, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[acc]);
+            sat_flush(satm);
         }
         if (elected) tma_store_wait_read();   // smem must outlive the bulk reads; the writes complete with the grid
     }

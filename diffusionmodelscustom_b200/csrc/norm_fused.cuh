@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
     // before any arithmetic (one dependent global load per iteration kept a single 16-byte load in flight per thread:
     // ncu long-scoreboard stall 7.0, 2.9 TB/s)
     const int nitems = nrows * 8;
+    float satm = 0.f;
     for (int i0 = threadIdx.x, k0 = 0; i0 < nitems; i0 += 4 * 256, k0 += 4) {
         uint4 av[4];
 #pragma unroll
@@ -197,11 +198,12 @@ __global__ void __launch_bounds__(256, 3) norm_fused_kernel(const NormParams p) 
                 }
             }
             uint4 o;
-            o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]);
-            o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+            o.x = pack_h2_acc(f[0], f[1], satm); o.y = pack_h2_acc(f[2], f[3], satm);
+            o.z = pack_h2_acc(f[4], f[5], satm); o.w = pack_h2_acc(f[6], f[7], satm);
             *reinterpret_cast<uint4*>(p.y + e) = o;
         }
     }
+    sat_flush(satm);
     cluster_wait_acquire();
 }
 

@@ -49,6 +49,25 @@ def test_conv_matches_torch(case, impl):
     assert G.rel_l2(G.to_nchw_f32(out), ref) < TOL
 
 
+@pytest.mark.parametrize("case", [("3x3_big", 2, 32, 64, 64, 3, 1, 1), ("1x1_stream", 70, 32, 64, 192, 1, 1, 0)], ids=["conv", "gemm_stream"])
+def test_saturation_counter_fires_in_the_gemm_epilogues(case):
+    """Outputs beyond +-65504 are clamped by the converter AND counted (per thread and tile since the epilogues track a running
+    maximum instead of testing every pair): zero for an in-range tensor, non-zero once a value leaves the fp16 range."""
+    _, B, H, Cin, Cout, R, stride, pad = case
+    g = torch.Generator().manual_seed(7)
+    x = _bf(torch.randn(B, Cin, H, H, generator=g))
+    w = _bf(torch.randn(Cout, Cin, R, R, generator=g) / math.sqrt(Cin * R * R))
+    for scale, want_clamp in ((1.0, False), (1.0e5, True)):
+        bias = torch.randn(Cout, generator=g) * scale
+        N.lib().b2d_saturation_count(1)
+        out = G.conv2d(G.nhwc_f16(x), G.pack_conv_weight(w), bias.cuda(), None, None, B, H, H, Cin, Cout, R, stride, pad, impl=0)
+        torch.cuda.synchronize()
+        cnt = int(N.lib().b2d_saturation_count(0))
+        assert (cnt > 0) == want_clamp, (scale, cnt)
+        assert torch.isfinite(out.float()).all()
+    N.lib().b2d_saturation_count(1)
+
+
 STREAM_CASES = [  # B, H, Cin, Cout, convt
     (2, 16, 64, 192, False), (3, 16, 128, 384, False), (5, 8, 64, 64, False), (2, 32, 128, 128, False),
     (1, 19 * 0 + 16, 64, 256, False), (3, 8, 64, 64, True), (2, 16, 128, 128, True), (70, 32, 64, 192, False)]
