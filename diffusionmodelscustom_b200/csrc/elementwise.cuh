@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restric
         }
     }
     uint32_t* stg = s_stage + warp * 1024;          // 32 pixels x 128 B
+    float satm = 0.f;
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt) {
         const int ho = ho0 + 2 * warp + mt;
@@ -324,10 +325,11 @@ __global__ void __launch_bounds__(256, 2) stem_mma_kernel(const float* __restric
                 v0 += s_vec[ch];
                 v1 += s_vec[ch + 1];
                 const int p = mt * 16 + ox;
-                stg[p * 32 + ((nt * 4 + tg) ^ ((p & 7) << 2))] = pack_h2(v0, v1);
+                stg[p * 32 + ((nt * 4 + tg) ^ ((p & 7) << 2))] = pack_h2_acc(v0, v1, satm);
             }
         }
     }
+    sat_flush(satm);
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
