@@ -563,8 +563,8 @@ struct Builder {
             auto tmq = std::make_shared<AttnTcMaps>();
             if (attn_tc_make_map(tmq.get(), qkv, B, L, C) != 0) { err = -1; return; }
             ops.meta(role + ".sdpa", "attn_tc", 4.0 * (double)L * L * C * B, 8.0 * rows * C);
-            // B2D_ATTN_V=1: round-1 kernel (3 CTAs/SM); 2: persistent two-tile kernel (attention_tc2.cuh); default 3: the
-            // four-CTAs-per-SM optimistic-maximum kernel (attention_tc3.cuh) — A/B switches, all three are parity-tested
+            // B2D_ATTN_V=1: round-1 kernel (3 CTAs/SM); 2: persistent two-tile kernel; 3: four CTAs per SM, optimistic maximum; 4: 32-key
+            // blocks; 6 / 7: self-issuing / named-barrier-issuer variants; default 8: attention_tc8.cuh — A/B switches, all parity-tested
             static const int attn_v = getenv("B2D_ATTN_V") ? atoi(getenv("B2D_ATTN_V")) : 8;
             const int sms = h->num_sms;
             if (attn_v == 2 && attn_tc2_supported(L, C, heads))

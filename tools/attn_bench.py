@@ -1,4 +1,4 @@
-"""Times b2d_op_attention alone (CUDA events) for the shapes that dominate the step.  B2D_NO_TC_ATTN=1 selects the mma.sync kernel; B2D_ATTN_V=1|2|3 and B2D_ATTN_POLY=0..4 select the tcgen05 variants."""
+"""Times b2d_op_attention alone (CUDA events) for the shapes that dominate the step.  B2D_NO_TC_ATTN=1 selects the mma.sync kernel; B2D_ATTN_V=1|2|3|4|6|7|8 (default 8) and B2D_ATTN_POLY=0..5 select the tcgen05 variants."""
 import sys, torch
 sys.path.insert(0, ".")
 from diffusionmodelscustom_b200 import _native as N
